@@ -1,0 +1,93 @@
+/* lb200.h -- C ABI of liblb200.so: the B200-native (sm_100a) backend of the
+ * latentblending branch-tree denoising hot path.
+ *
+ * The reference (lunarring/latentblending @ fd5916a) has no FFI: its operator
+ * seam is the duck-typed ``DiffusersHolder`` Python object.  Every entry point
+ * below names the reference call it replaces (file:line under
+ * /root/reference/latentblending/).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C types only; every ``dev`` pointer is a device pointer on the
+ *    context's CUDA device; ``stream`` is a ``cudaStream_t`` passed as void*.
+ *  - all calls enqueue asynchronously on ``stream``; no host sync, no
+ *    allocation inside hot calls (the caller owns every buffer, including the
+ *    workspaces whose sizes the *_workspace_bytes calls report).
+ *  - return 0 on success, non-zero on error; lb_last_error() describes the
+ *    last failure on the calling thread.
+ *  - fp16 means IEEE binary16 (``__half``).  Activations are NHWC
+ *    ([batch*height*width, channels] row-major); latents are NCHW like the
+ *    reference's ``[1,4,h,w]`` tensors.
+ */
+#ifndef LB200_H
+#define LB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB_ABI_VERSION 1
+
+typedef struct lb_ctx lb_ctx;
+
+int         lb_abi_version(void);
+const char* lb_last_error(void);
+/* one context per device; not thread-safe per context */
+int lb_ctx_create(int device, lb_ctx** out);
+int lb_ctx_destroy(lb_ctx* ctx);
+int lb_ctx_sm_count(lb_ctx* ctx);
+
+/* ---- K1: latent mixing ----------------------------------------------------
+ * lb_slerp_rows: ``rows`` independent whole-row spherical interpolations
+ *   out[r] = slerp(p0[r], p1[r], fract)   (fp64 arithmetic, result cast
+ *   fp64->fp32->dtype, exactly utils.py:47-71).
+ * Replaces: utils.py:29-71 interpolate_spherical; the 30-iteration parental
+ * mix loop blending_engine.py:442-450 (rows = steps x branches; the None rows
+ * are simply not passed); the in-loop crossfeed diffusers_holder.py:322-324
+ * (rows = 1).
+ *   dtype: 0 = fp16, 1 = fp32.  n = elements per row; row r starts at
+ *   base + r*stride_{0,1,out} elements.  fract_rows_dev (device, fp64[rows])
+ *   overrides ``fract`` per row when non-NULL.
+ *   workspace_dev: lb_slerp_workspace_bytes(rows, n) bytes (may be NULL when
+ *   that returns 0).
+ */
+size_t lb_slerp_workspace_bytes(int64_t rows, int64_t n);
+int lb_slerp_rows(lb_ctx* ctx, const void* p0_dev, const void* p1_dev, void* out_dev,
+                  int64_t rows, int64_t n, int64_t stride0, int64_t stride1, int64_t stride_out,
+                  int dtype, double fract, const double* fract_rows_dev,
+                  void* workspace_dev, void* stream);
+
+/* lb_lerp: out = (1-f)*p0 + f*p1 elementwise, per-op rounding in ``dtype``
+ * like torch (utils.py:97 on the 4-tuple text embeddings,
+ * blending_engine.py:643-654). */
+int lb_lerp(lb_ctx* ctx, const void* p0_dev, const void* p1_dev, void* out_dev,
+            int64_t n, int dtype, double fract, void* stream);
+
+/* ---- K9: scheduler arithmetic around the UNet ------------------------------
+ * lb_scale_model_input: x_in[b] = fp16(x / divisor) for b < batch (CFG
+ * duplicate, diffusers_holder.py:328-330; divisor = sqrt(sigma^2+1) in fp32).
+ */
+int lb_scale_model_input(lb_ctx* ctx, const void* latents_dev, void* out_dev,
+                         int64_t n, int batch, float divisor, void* stream);
+
+/* lb_cfg_euler_step: classifier-free-guidance combine + Euler(-ancestral) step
+ * + trajectory store, with the reference's per-op fp16 roundings reproduced:
+ *   eps = u + g*(t-u)                        diffusers_holder.py:347-349
+ *   x'  = x + ((x-(x-sigma*eps))/sigma)*dt   diffusers_holder.py:356 (Euler)
+ *   x'' = x' + noise*sigma_up                (ancestral only; noise may be NULL)
+ * eps_dev holds [2,n] (uncond, text) when use_cfg else [1,n].
+ * Writes the new latents to out_dev and, if non-NULL, a clone to traj_dev
+ * (``list_latents_out.append(latents.clone())``, diffusers_holder.py:359).
+ */
+int lb_cfg_euler_step(lb_ctx* ctx, const void* latents_dev, const void* eps_dev,
+                      const void* noise_dev, void* out_dev, void* traj_dev,
+                      int64_t n, int use_cfg, float guidance, float sigma, float dt,
+                      float sigma_up, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LB200_H */

@@ -1,0 +1,89 @@
+"""ctypes binding of liblb200.so (C ABI declared in include/lb200.h).
+
+The product path has NO fallback: if the shared library is missing or a call
+fails, an exception is raised.  PyTorch is only used by callers for device
+memory and streams; nothing here takes or returns torch types except through
+``.data_ptr()`` integers.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblb200.so")
+
+c_void_p, c_int, c_int64, c_float, c_double, c_size_t = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_size_t)
+
+# name -> (restype, argtypes); mirrors include/lb200.h one to one
+SIGNATURES = {
+    "lb_abi_version": (c_int, []),
+    "lb_last_error": (ctypes.c_char_p, []),
+    "lb_ctx_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    "lb_ctx_destroy": (c_int, [c_void_p]),
+    "lb_ctx_sm_count": (c_int, [c_void_p]),
+    "lb_slerp_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "lb_slerp_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                              c_int, c_double, c_void_p, c_void_p, c_void_p]),
+    "lb_lerp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p]),
+    "lb_scale_model_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
+    "lb_cfg_euler_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                  c_float, c_float, c_float, c_float, c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_ctx = {}
+
+
+class LB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load liblb200.so (once).  Raises LB200Error if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise LB200Error(
+                f"{LIB_PATH} not found: build it with `python -m latentblending_b200.build` "
+                "(there is no CPU or PyTorch fallback for the CUDA hot path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)       # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if lib.lb_abi_version() != 1:
+            raise LB200Error("liblb200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().lb_last_error()
+        raise LB200Error(f"{what} failed ({status}): {msg.decode() if msg else '?'}")
+
+
+def ctx(device_index=0):
+    """The per-device context handle (created on first use)."""
+    lib = load()
+    if device_index not in _ctx:
+        h = c_void_p()
+        check(lib.lb_ctx_create(int(device_index), ctypes.byref(h)), "lb_ctx_create")
+        _ctx[device_index] = h
+    return _ctx[device_index]
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

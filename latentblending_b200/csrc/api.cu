@@ -1,0 +1,41 @@
+// api.cu -- context and error plumbing of the C ABI (include/lb200.h).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void lb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int lb_abi_version(void) { return LB_ABI_VERSION; }
+extern "C" const char* lb_last_error(void) { return g_err; }
+
+extern "C" int lb_ctx_create(int device, lb_ctx** out) {
+    LB_REQUIRE(out != nullptr, "lb_ctx_create: null out pointer");
+    int count = 0;
+    LB_CHECK_CUDA(cudaGetDeviceCount(&count));
+    LB_REQUIRE(device >= 0 && device < count, "lb_ctx_create: device %d out of range (%d devices)", device, count);
+    cudaDeviceProp prop;
+    LB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    LB_REQUIRE(prop.major == 10, "lb_ctx_create: liblb200 is built for sm_100a only; device %d is sm_%d%d",
+               device, prop.major, prop.minor);
+    lb_ctx* c = new lb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    c->tmap_encode = nullptr;
+    *out = c;
+    return 0;
+}
+
+extern "C" int lb_ctx_destroy(lb_ctx* ctx) {
+    delete ctx;
+    return 0;
+}
+
+extern "C" int lb_ctx_sm_count(lb_ctx* ctx) { return ctx ? ctx->sm_count : -1; }

@@ -1,0 +1,118 @@
+"""GPU parity: K1 (slerp/lerp) and K9 (CFG + Euler step) through the C ABI
+against the CPU oracle and the reference-generated golden vectors.
+Bar: bit-exact (the kernels reproduce the reference's rounding chain)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_slerp_golden_bit_exact():
+    from latentblending_b200 import utils
+    z = np.load(os.path.join(GOLD, "slerp.npz"))
+    for k in range(int(z["n_cases"])):
+        p0 = torch.from_numpy(z[f"p0_{k}"]).cuda()
+        p1 = torch.from_numpy(z[f"p1_{k}"]).cuda()
+        out = utils.interpolate_spherical(p0, p1, float(z[f"f_{k}"])).cpu()
+        ref = torch.from_numpy(z[f"out_{k}"])
+        assert out.dtype == ref.dtype
+        assert torch.equal(out, ref), f"case {k}: {(out != ref).sum().item()} mismatches"
+
+
+@pytest.mark.parametrize("n", [8, 1000, 1024, 4 * 64 * 64, 4 * 128 * 128, 4 * 128 * 128 + 8, 4 * 160 * 160, 300001])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_slerp_rows_vs_oracle(n, dtype):
+    from latentblending_b200 import ops
+    from oracle import mixing
+    g = torch.Generator().manual_seed(n)
+    rows = 5
+    p0 = (torch.randn(rows, n, generator=g) * 3).to(dtype)
+    p1 = torch.randn(rows, n, generator=g).to(dtype)
+    out = ops.slerp_rows(p0.cuda(), p1.cuda(), 0.37).cpu()
+    for r in range(rows):
+        ref = mixing.interpolate_spherical(p0[r], p1[r], 0.37)
+        assert torch.equal(out[r], ref), f"row {r}: {(out[r] != ref).sum().item()} mismatches"
+
+
+def test_slerp_strided_rows_and_per_row_fract():
+    from latentblending_b200 import ops
+    from oracle import mixing
+    g = torch.Generator().manual_seed(3)
+    n = 4 * 32 * 32
+    big0 = torch.randn(6, 2, n, generator=g).half()
+    big1 = torch.randn(6, 2, n, generator=g).half()
+    fr = torch.tensor([0.0, 0.1, 0.5, 0.9, 1.0, 0.33], dtype=torch.float64)
+    a, b = big0.cuda()[:, 1], big1.cuda()[:, 0]      # row stride 2n
+    out = ops.slerp_rows(a, b, 0.0, fract_rows=fr.cuda()).cpu()
+    for r in range(6):
+        assert torch.equal(out[r], mixing.interpolate_spherical(big0[r, 1], big1[r, 0], float(fr[r])))
+
+
+def test_slerp_endpoints_and_empty():
+    from latentblending_b200 import ops, utils
+    g = torch.Generator().manual_seed(5)
+    p0 = torch.randn(1, 4, 16, 16, generator=g).half().cuda()
+    p1 = torch.randn(1, 4, 16, 16, generator=g).half().cuda()
+    # f=0 -> p0, f=1 -> p1 up to the 1e-7 clamp (<= 1 fp16 ulp)
+    assert (utils.interpolate_spherical(p0, p1, 0.0).float() - p0.float()).abs().max() <= 2e-3
+    assert (utils.interpolate_spherical(p0, p1, 1.0).float() - p1.float()).abs().max() <= 2e-3
+    e = torch.empty(0, 64, dtype=torch.float16, device="cuda")
+    assert ops.slerp_rows(e, e, 0.5).shape == (0, 64)
+
+
+def test_lerp_vs_oracle():
+    from latentblending_b200 import utils
+    from oracle import mixing
+    z = np.load(os.path.join(GOLD, "slerp.npz"))
+    a, b = torch.from_numpy(z["lin_a"]), torch.from_numpy(z["lin_b"])
+    assert torch.equal(utils.interpolate_linear(a.cuda(), b.cuda(), 0.3).cpu(), torch.from_numpy(z["lin_out"]))
+    g = torch.Generator().manual_seed(9)
+    for dt in (torch.float16, torch.float32):
+        x, y = torch.randn(1, 77, 2048, generator=g).to(dt), torch.randn(1, 77, 2048, generator=g).to(dt)
+        for f in (0.0, 0.5, 0.8125, 1.0):
+            assert torch.equal(utils.interpolate_linear(x.cuda(), y.cuda(), f).cpu(),
+                               mixing.interpolate_linear(x, y, f))
+
+
+@pytest.mark.parametrize("turbo", [False, True])
+@pytest.mark.parametrize("hw", [16, 64, 128, 9])
+def test_cfg_euler_step_bit_exact(turbo, hw):
+    from latentblending_b200 import ops
+    from oracle.schedulers import EulerAncestralDiscrete, EulerDiscrete
+    sched = EulerAncestralDiscrete() if turbo else EulerDiscrete()
+    N = 4 if turbo else 30
+    sched.set_timesteps(N)
+    g = torch.Generator().manual_seed(hw + turbo)
+    for i in ([0, 1, 3] if turbo else [0, 7, 15, 29]):
+        x = (torch.randn(1, 4, hw, hw, generator=g) * float(sched.sigmas[i] + 1)).half()
+        eps = torch.randn(2, 4, hw, hw, generator=g).half()
+        noise = torch.randn(1, 4, hw, hw, generator=g).half() if turbo else None
+        gsc = np.float64(3.37)
+        # oracle, op by op (oracle/holder.py loop body)
+        x_in_ref = sched.scale_model_input(torch.cat([x] * 2), i)
+        e_u, e_t = eps.chunk(2)
+        e = e_u + gsc * (e_t - e_u)
+        ref = sched.step(e, i, x, noise=noise)
+        ref_nocfg = sched.step(eps[:1], i, x, noise=noise)
+        # CUDA
+        sigma = sched.sigmas[i]
+        div = float((sigma ** 2 + 1) ** 0.5)
+        x_in = ops.scale_model_input(x.cuda(), 2, div).cpu()
+        assert torch.equal(x_in, x_in_ref)
+        if turbo:
+            s_up, s_down = sched.sigma_up_down(i)
+            dt, sup = float(s_down - sigma), float(s_up)
+        else:
+            dt, sup = float(sched.sigmas[i + 1] - sigma), 0.0
+        traj = torch.empty_like(x).cuda()
+        out = ops.cfg_euler_step(x.cuda(), eps.cuda(), gsc, float(sigma), dt, sup,
+                                 noise=None if noise is None else noise.cuda(), traj=traj).cpu()
+        assert torch.equal(out, ref), f"step {i}: {(out != ref).sum().item()} mismatches"
+        assert torch.equal(traj.cpu(), ref)
+        out1 = ops.cfg_euler_step(x.cuda(), eps[:1].contiguous().cuda(), 0.0, float(sigma), dt, sup,
+                                  noise=None if noise is None else noise.cuda()).cpu()
+        assert torch.equal(out1, ref_nocfg)
