@@ -69,4 +69,4 @@ class OraclePipe:
     def prepare_latents(self, h_lat, w_lat, seed, dtype=torch.float16):
         g = torch.Generator().manual_seed(int(seed))
         lat = torch.randn(1, self.unet_cfg.in_channels, h_lat, w_lat, generator=g).to(dtype)
-        return lat * self.scheduler.init_noise_sigma
+        return lat * self.scheduler.init_noise_sigma.to(dtype)

@@ -13,12 +13,23 @@ Pinned by the known-answer vectors in SURVEY.md appendix C
 (tests/test_oracle_schedulers.py): sigma_max 14.6146 / sigma_min 0.0292.
 
 All tensor arithmetic is written as individual torch ops on purpose: with fp16
-latents every op rounds to fp16 exactly like the reference stack does (fp32
-op-math on the fp32 0-dim sigma, fp16 store), which is what the fused CUDA
-step kernel has to reproduce bit for bit.
+latents every op rounds to fp16 exactly like the reference stack does, which is
+what the fused CUDA step kernel has to reproduce bit for bit.
+
+Scalar semantics (measured, profiles/r01_probe_scalar_semantics.txt): on the
+reference's real stack the sigmas live on the CUDA device, and PyTorch's CUDA
+binary kernels cast an fp32 0-dim *CUDA tensor* operand to the fp16 common
+dtype before the fp32 op-math (Python scalars such as guidance_scale stay fp32).
+PyTorch's CPU kernels do this only for some operand orders, so the oracle makes
+the cast explicit (``_s``) to be device-independent and faithful to CUDA.
 """
 import numpy as np
 import torch
+
+
+def _s(scalar, like):
+    """0-dim fp32 scheduler scalar as the CUDA stack sees it next to ``like``."""
+    return scalar.to(like.dtype)
 
 
 def _train_sigmas(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
@@ -64,14 +75,14 @@ class EulerDiscrete:
 
     def scale_model_input(self, sample, i):
         sigma = self.sigmas[i]
-        return sample / ((sigma ** 2 + 1) ** 0.5)
+        return sample / _s((sigma ** 2 + 1) ** 0.5, sample)
 
     def step(self, model_output, i, sample, noise=None):
         sigma = self.sigmas[i]
-        pred_original = sample - sigma * model_output
-        derivative = (sample - pred_original) / sigma
+        pred_original = sample - _s(sigma, sample) * model_output
+        derivative = (sample - pred_original) / _s(sigma, sample)
         dt = self.sigmas[i + 1] - sigma
-        return sample + derivative * dt
+        return sample + derivative * _s(dt, sample)
 
 
 class EulerAncestralDiscrete(EulerDiscrete):
@@ -104,11 +115,11 @@ class EulerAncestralDiscrete(EulerDiscrete):
         """``noise`` must be injected (the reference draws it from the global
         generator because generator=None, diffusers_holder.py:192,255,356)."""
         sigma = self.sigmas[i]
-        pred_original = sample - sigma * model_output
+        pred_original = sample - _s(sigma, sample) * model_output
         s_up, s_down = self.sigma_up_down(i)
-        derivative = (sample - pred_original) / sigma
+        derivative = (sample - pred_original) / _s(sigma, sample)
         dt = s_down - sigma
-        prev = sample + derivative * dt
+        prev = sample + derivative * _s(dt, sample)
         if noise is None:
             noise = torch.zeros_like(model_output)
-        return prev + noise * s_up
+        return prev + noise * _s(s_up, sample)
