@@ -87,6 +87,38 @@ int lb_cfg_euler_step(lb_ctx* ctx, const void* latents_dev, const void* eps_dev,
                       int64_t n, int use_cfg, float guidance, float sigma, float dt,
                       float sigma_up, void* stream);
 
+/* ---- K7 / K4: tensor-core GEMM and implicit-GEMM convolution ----------------
+ * out[M,N] = epilogue( conv_taps(a0)[M, taps*a0_c] | a1[M, a1_c] ) x w[N, K]^T ),
+ * fp16 operands, fp32 accumulation in TMEM (tcgen05.mma), M = B*H*W rows of an
+ * NHWC activation.  taps = 1: Linear / 1x1 conv; taps = 9: 3x3 conv, stride 1,
+ * zero padding 1 (weights pre-packed [N][ky][kx][a0_c]).  a1 (optional) is a
+ * second 1x1 input appended along K (the resnet shortcut conv folded into
+ * conv2).  Epilogue mode 0: + bias[n] + bias2[b][n] (time-embedding projection)
+ * + res[row][n]; mode 1: GEGLU, N accumulators -> N/2 outputs (weight rows
+ * interleaved per 128-column tile: 64 value rows then their 64 gate rows).
+ * Replaces the cuBLAS / cuDNN calls under pipe.unet(...)
+ * (diffusers_holder.py:336-344).  Constraints: a0_c, a1_c multiples of 64;
+ * N multiple of 8; W >= 128 or W, (H) powers of two; 16-byte aligned bases.
+ */
+typedef struct lb_gemm_desc {
+    const void* a0; int64_t a0_ld; int32_t a0_c;
+    const void* a1; int64_t a1_ld; int32_t a1_c;
+    int32_t B, H, W;
+    int32_t taps;
+    const void* w; int64_t w_ld;
+    int32_t N;
+    const void* bias;
+    const void* bias2; int64_t bias2_ld;
+    const void* res; int64_t res_ld;
+    void* out; int64_t out_ld;
+    int32_t mode;
+} lb_gemm_desc;
+int lb_gemm(lb_ctx* ctx, const lb_gemm_desc* desc, void* stream);
+
+/* Reads and clears the device-side protocol-error flag the pipelined kernels
+ * set before trapping (0 = no error).  Synchronises the device: debug only. */
+int lb_ctx_error_flag(lb_ctx* ctx, int* out_code);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,21 @@ LIB_PATH = os.path.join(_HERE, "liblb200.so")
 c_void_p, c_int, c_int64, c_float, c_double, c_size_t = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_size_t)
 
+class GemmDesc(ctypes.Structure):
+    """lb_gemm_desc of include/lb200.h."""
+    _fields_ = [("a0", c_void_p), ("a0_ld", c_int64), ("a0_c", ctypes.c_int32),
+                ("a1", c_void_p), ("a1_ld", c_int64), ("a1_c", ctypes.c_int32),
+                ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+                ("taps", ctypes.c_int32),
+                ("w", c_void_p), ("w_ld", c_int64),
+                ("N", ctypes.c_int32),
+                ("bias", c_void_p),
+                ("bias2", c_void_p), ("bias2_ld", c_int64),
+                ("res", c_void_p), ("res_ld", c_int64),
+                ("out", c_void_p), ("out_ld", c_int64),
+                ("mode", ctypes.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/lb200.h one to one
 SIGNATURES = {
     "lb_abi_version": (c_int, []),
@@ -29,6 +44,8 @@ SIGNATURES = {
     "lb_scale_model_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
     "lb_cfg_euler_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                   c_float, c_float, c_float, c_float, c_void_p]),
+    "lb_gemm": (c_int, [c_void_p, ctypes.POINTER(GemmDesc), c_void_p]),
+    "lb_ctx_error_flag": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
 }
 
 _lib = None

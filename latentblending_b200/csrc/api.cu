@@ -3,6 +3,8 @@
 
 #include "common.cuh"
 
+int* lb_err_flag(lb_ctx* ctx);
+
 static thread_local char g_err[1024] = "";
 
 void lb_set_error(const char* fmt, ...) {
@@ -29,11 +31,29 @@ extern "C" int lb_ctx_create(int device, lb_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     c->tmap_encode = nullptr;
+    c->err_flag_dev = nullptr;
+    LB_CHECK_CUDA(cudaSetDevice(device));
+    LB_CHECK_CUDA(cudaMalloc(&c->err_flag_dev, sizeof(int)));
+    LB_CHECK_CUDA(cudaMemset(c->err_flag_dev, 0, sizeof(int)));
     *out = c;
     return 0;
 }
 
+int* lb_err_flag(lb_ctx* ctx) { return ctx->err_flag_dev; }
+
+extern "C" int lb_ctx_error_flag(lb_ctx* ctx, int* out_code) {
+    LB_REQUIRE(ctx && out_code, "lb_ctx_error_flag: null argument");
+    cudaError_t e = cudaMemcpy(out_code, ctx->err_flag_dev, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        lb_set_error("lb_ctx_error_flag: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    cudaMemset(ctx->err_flag_dev, 0, sizeof(int));
+    return 0;
+}
+
 extern "C" int lb_ctx_destroy(lb_ctx* ctx) {
+    if (ctx && ctx->err_flag_dev) cudaFree(ctx->err_flag_dev);
     delete ctx;
     return 0;
 }

@@ -1,0 +1,49 @@
+// gemm_sm100.cuh -- host-side plan object of the tcgen05 GEMM / implicit-GEMM conv kernel (K7 + K4).
+#pragma once
+#include "common.cuh"
+
+// Mirrors lb_gemm_desc of include/lb200.h (kept in sync by hand; plain C layout).
+struct GemmDesc {
+    const void* a0; int64_t a0_ld; int32_t a0_c;
+    const void* a1; int64_t a1_ld; int32_t a1_c;
+    int32_t B, H, W;
+    int32_t taps;
+    const void* w; int64_t w_ld;
+    int32_t N;
+    const void* bias;
+    const void* bias2; int64_t bias2_ld;
+    const void* res; int64_t res_ld;
+    void* out; int64_t out_ld;
+    int32_t mode;   // 0 linear epilogue, 1 GEGLU (N accumulators -> N/2 outputs)
+};
+
+constexpr int kGemmMaxSegs = 12;
+
+struct alignas(64) GemmParams {
+    CUtensorMap tmA[2];
+    CUtensorMap tmB;
+    int num_segs;
+    int seg_map[kGemmMaxSegs], seg_dy[kGemmMaxSegs], seg_dx[kGemmMaxSegs], seg_kb[kGemmMaxSegs];
+    int total_kb;
+    int W, H, B;
+    int tw, th, tb;
+    int tiles_x, tiles_y, tiles_m, tiles_n;
+    int N;
+    int mode;
+    __half* out; long long ldo;
+    const __half* bias;
+    const __half* bias2; long long bias2_ld;
+    const __half* res; long long ldr;
+    int* err_flag;
+};
+
+struct GemmPlan {
+    GemmParams p;
+    int bn;        // N tile: 64 / 128 / 160 / 256
+    int grid;
+    int smem_bytes;
+};
+
+int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan);
+int gemm_plan_launch(const GemmPlan& plan, cudaStream_t st);
+int* lb_err_flag(lb_ctx* ctx);

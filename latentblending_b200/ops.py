@@ -80,3 +80,40 @@ def cfg_euler_step(latents, eps, guidance, sigma, dt, sigma_up=0.0, noise=None, 
                                          int(use_cfg), float(np.float32(guidance)), float(sigma), float(dt),
                                          float(sigma_up), stream_ptr()), "lb_cfg_euler_step")
     return out
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def gemm(a0, w, N, B, H, W, taps=1, a0_c=None, a1=None, a1_c=None, bias=None, bias2=None, res=None, out=None,
+         mode=0, out_cols=None):
+    """Tensor-core GEMM / implicit-GEMM conv (lb_gemm).  a0: NHWC activation viewed as
+    [B*H*W, >=a0_c] (row stride = a0.stride(0)); w: [N, K] packed weights."""
+    dev = _dev(a0)
+    M = B * H * W
+    a0_c = a0.shape[-1] if a0_c is None else a0_c
+    n_out = (N // 2 if mode == 1 else N) if out_cols is None else out_cols
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float16, device=a0.device)
+    d = _cabi.GemmDesc()
+    d.a0, d.a0_ld, d.a0_c = _p(a0), a0.stride(-2), a0_c
+    if a1 is not None:
+        d.a1, d.a1_ld, d.a1_c = _p(a1), a1.stride(-2), (a1.shape[-1] if a1_c is None else a1_c)
+    d.B, d.H, d.W, d.taps = B, H, W, taps
+    d.w, d.w_ld, d.N = _p(w), w.stride(0), N
+    d.bias = _p(bias)
+    if bias2 is not None:
+        d.bias2, d.bias2_ld = _p(bias2), bias2.stride(0)
+    if res is not None:
+        d.res, d.res_ld = _p(res), res.stride(-2)
+    d.out, d.out_ld, d.mode = _p(out), out.stride(-2), mode
+    check(_cabi.load().lb_gemm(ctx(dev), d, stream_ptr()), "lb_gemm")
+    return out
+
+
+def error_flag(dev=0):
+    import ctypes
+    code = ctypes.c_int(0)
+    check(_cabi.load().lb_ctx_error_flag(ctx(dev), ctypes.byref(code)), "lb_ctx_error_flag")
+    return code.value
