@@ -115,6 +115,61 @@ typedef struct lb_gemm_desc {
 } lb_gemm_desc;
 int lb_gemm(lb_ctx* ctx, const lb_gemm_desc* desc, void* stream);
 
+/* ---- K8: fused attention, head_dim 64 ----------------------------------------
+ * out[b, s, h*64+d] = softmax(Q K^T * scale) V per (batch, head); Q/K/V are
+ * column slices of row-major [B*S, ld] fp16 buffers: head h of Q lives in
+ * columns [q_col0 + 64h, q_col0 + 64h + 64) etc., so a fused QKV projection
+ * ([.., 3C]) or a fused cross-attention KV projection ([B*77, 2C]) is consumed
+ * in place.  Replaces F.scaled_dot_product_attention (diffusers AttnProcessor2_0)
+ * under pipe.unet(...), diffusers_holder.py:336-344.  No mask, no dropout.
+ */
+typedef struct lb_attn_desc {
+    const void* q; int64_t q_ld; int32_t q_col0;
+    const void* k; int64_t k_ld; int32_t k_col0;
+    const void* v; int64_t v_ld; int32_t v_col0;
+    void* out; int64_t out_ld;
+    int32_t B, heads, Sq, Skv, head_dim;
+    float scale;
+} lb_attn_desc;
+int lb_attention(lb_ctx* ctx, const lb_attn_desc* desc, void* stream);
+
+/* ---- K5 / K6: normalisation -----------------------------------------------------
+ * lb_groupnorm: torch.nn.GroupNorm(groups, C, eps) over an NHWC activation
+ * [B*HW, C] (row stride ld), optionally followed by SiLU; fp32 statistics.
+ * lb_layernorm: torch.nn.LayerNorm(C, eps) over rows.  Both replace the norm
+ * layers inside pipe.unet(...) (diffusers_holder.py:336-344).
+ */
+size_t lb_groupnorm_workspace_bytes(lb_ctx* ctx, int B, int HW, int groups);
+int lb_groupnorm(lb_ctx* ctx, const void* x, int64_t ld, int B, int HW, int C, int groups,
+                 const void* gamma, const void* beta, float eps, int silu,
+                 void* out, int64_t ldo, void* workspace, void* stream);
+int lb_layernorm(lb_ctx* ctx, const void* x, int64_t ld, int64_t rows, int C,
+                 const void* gamma, const void* beta, float eps, void* out, int64_t ldo, void* stream);
+
+/* ---- K3 / K2: embeddings and the boundary convolutions ------------------------------
+ * lb_embed_inputs: sinusoidal timestep features [B,dim_t] and the text_time
+ *   added-condition vector [B, pooled + 6*dim_a] (diffusers get_timestep_embedding,
+ *   flip_sin_to_cos, freq_shift 0).
+ * lb_linear_small: out = act_out(act_in(x) W^T + bias) (+ addend) for M <= 16 rows
+ *   (time_embedding, add_embedding, all resnet time_emb_proj in one launch);
+ *   act: 0 none, 1 SiLU.
+ * lb_conv_in / lb_conv_out: the 4->C0 and C0->4 3x3 convolutions at the NCHW
+ *   latent boundary.  lb_upsample2x: nearest 2x (Upsample2D).  lb_im2col_s2: patch
+ *   matrix of the stride-2 Downsample2D convs (then lb_gemm).
+ */
+int lb_embed_inputs(lb_ctx* ctx, float t, const void* text_embeds, const void* time_ids, int B,
+                    int dim_t, int pooled, int dim_a, void* temb_in, void* add_in, void* stream);
+int lb_linear_small(lb_ctx* ctx, const void* x, int64_t ldx, int M, int K, const void* w, int64_t ldw,
+                    const void* bias, const void* addend, int64_t ldadd, int act_in, int act_out,
+                    void* out, int64_t ldo, int N, void* stream);
+int lb_conv_in(lb_ctx* ctx, const void* x_nchw, int B, int Cin, int H, int W, const void* w_packed,
+               const void* bias, int Cout, void* out, int64_t ldo, void* stream);
+int lb_conv_out(lb_ctx* ctx, const void* x, int64_t ld, int B, int Cin, int H, int W, const void* w_packed,
+                const void* bias, int Cout, void* out_nchw, void* stream);
+int lb_upsample2x(lb_ctx* ctx, const void* x, int64_t ld, int B, int H, int W, int C, void* out, int64_t ldo,
+                  void* stream);
+int lb_im2col_s2(lb_ctx* ctx, const void* x, int64_t ld, int B, int H, int W, int C, void* out, void* stream);
+
 /* Reads and clears the device-side protocol-error flag the pipelined kernels
  * set before trapping (0 = no error).  Synchronises the device: debug only. */
 int lb_ctx_error_flag(lb_ctx* ctx, int* out_code);

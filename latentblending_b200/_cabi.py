@@ -30,6 +30,16 @@ class GemmDesc(ctypes.Structure):
                 ("mode", ctypes.c_int32)]
 
 
+class AttnDesc(ctypes.Structure):
+    """lb_attn_desc of include/lb200.h."""
+    _fields_ = [("q", c_void_p), ("q_ld", c_int64), ("q_col0", ctypes.c_int32),
+                ("k", c_void_p), ("k_ld", c_int64), ("k_col0", ctypes.c_int32),
+                ("v", c_void_p), ("v_ld", c_int64), ("v_col0", ctypes.c_int32),
+                ("out", c_void_p), ("out_ld", c_int64),
+                ("B", ctypes.c_int32), ("heads", ctypes.c_int32), ("Sq", ctypes.c_int32), ("Skv", ctypes.c_int32),
+                ("head_dim", ctypes.c_int32), ("scale", c_float)]
+
+
 # name -> (restype, argtypes); mirrors include/lb200.h one to one
 SIGNATURES = {
     "lb_abi_version": (c_int, []),
@@ -46,6 +56,22 @@ SIGNATURES = {
                                   c_float, c_float, c_float, c_float, c_void_p]),
     "lb_gemm": (c_int, [c_void_p, ctypes.POINTER(GemmDesc), c_void_p]),
     "lb_ctx_error_flag": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
+    "lb_attention": (c_int, [c_void_p, ctypes.POINTER(AttnDesc), c_void_p]),
+    "lb_groupnorm_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    "lb_groupnorm": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
+                             c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "lb_layernorm": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_float, c_void_p,
+                             c_int64, c_void_p]),
+    "lb_embed_inputs": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p]),
+    "lb_linear_small": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p,
+                                c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "lb_conv_in": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                           c_int64, c_void_p]),
+    "lb_conv_out": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                            c_void_p, c_void_p]),
+    "lb_upsample2x": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "lb_im2col_s2": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,290 @@
+// attn_sm100.cu -- K8: fused softmax(Q K^T / sqrt(d)) V for head dim 64 on tcgen05 (sm_100a).
+//
+// Replaces F.scaled_dot_product_attention under diffusers' AttnProcessor2_0 in
+// every transformer block of the SDXL UNet (call site
+// latentblending/diffusers_holder.py:336-344): self-attention (S = 4096 / 1024,
+// Q,K,V slices of one fused-QKV activation) and cross-attention to the 77 text
+// tokens (K,V slices of a [B,77,2C] projection).  fp16 in, fp32 softmax, fp16 out.
+//
+// One CTA = 128 query rows of one (batch, head); two CTAs per SM so one CTA's
+// softmax overlaps the other's MMAs.  Per 128-key tile:
+//   S = Q K^T   tcgen05.mma M128 N128 K64, Q/K K-major 128B-swizzled TMA tiles, S in TMEM
+//   softmax     warps 2-5, one query row per thread: tcgen05.ld S, online max/sum in
+//               the exp2 domain, P (fp16) written to smem in the UMMA K-major layout
+//   O_j = P V   tcgen05.mma M128 N64 K128, V consumed MN-major straight from its TMA tile
+//   O = alpha*O + O_j in registers (fp32), normalised by the row sum at the end.
+// Bound: tensor pipe / MUFU.EX2; algorithmic FLOPs = 4*Sq*Skv*64 per head.
+#include "common.cuh"
+#include "sm100.cuh"
+
+using namespace sm100;
+
+struct alignas(64) AttnParams {
+    CUtensorMap tmQ, tmK, tmV;     // 3-D maps (columns, rows, batch), box (64, 128, 1), 128B swizzle
+    int Sq, Skv, heads, B;
+    int q_col0, k_col0, v_col0;    // column of head 0 inside each buffer
+    __half* out; long long ldo;    // [B*Sq, heads*64]
+    float scale_log2;              // softmax scale * log2(e)
+    int* err_flag;
+};
+
+namespace {
+
+constexpr int kD = 64, kBQ = 128, kBKV = 128;
+constexpr int kTileBytes = 128 * 64 * 2;      // 16 KiB: Q, K, V tiles
+constexpr int kPBytes = 128 * 128 * 2;        // 32 KiB
+constexpr int kAttnSmem = 3 * kTileBytes + kPBytes + 1024 + 128;
+constexpr int kAttnThreads = 192;
+constexpr uint32_t kTmemCols = 256;           // S: cols [0,128), O_j: cols [128,192)
+
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + kTileBytes;
+    uint8_t* sV = smem + 2 * kTileBytes;
+    uint8_t* sP = smem + 3 * kTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kTileBytes + kPBytes);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;
+    uint64_t* v_full = bars + 2;
+    uint64_t* k_empty = bars + 3;
+    uint64_t* v_empty = bars + 4;
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_ready = bars + 6;
+    uint64_t* o_full = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
+    const int nkv = (p.Skv + kBKV - 1) / kBKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmQ);
+        tma_prefetch_desc(&p.tmK);
+        tma_prefetch_desc(&p.tmV);
+        mbar_init(q_full, 1);
+        mbar_init(k_full, 1);
+        mbar_init(v_full, 1);
+        mbar_init(k_empty, 1);
+        mbar_init(v_empty, 1);
+        mbar_init(s_full, 1);
+        mbar_init(p_ready, 4);
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer ----------------
+        mbar_expect_tx(q_full, kTileBytes);
+        tma_load_3d(sQ, &p.tmQ, q_full, p.q_col0 + head * kD, q0, b);
+        for (int j = 0; j < nkv; ++j) {
+            const uint32_t ph = j & 1;
+            mbar_wait(k_empty, ph ^ 1, p.err_flag, 11);
+            mbar_expect_tx(k_full, kTileBytes);
+            tma_load_3d(sK, &p.tmK, k_full, p.k_col0 + head * kD, j * kBKV, b);
+            mbar_wait(v_empty, ph ^ 1, p.err_flag, 12);
+            mbar_expect_tx(v_full, kTileBytes);
+            tma_load_3d(sV, &p.tmV, v_full, p.v_col0 + head * kD, j * kBKV, b);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, 0, 1);   // B (= V) is MN-major
+        const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+        mbar_wait(q_full, 0, p.err_flag, 13);
+        for (int j = 0; j < nkv; ++j) {
+            const uint32_t ph = j & 1;
+            mbar_wait(k_full, ph, p.err_flag, 14);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < kD / 16; ++k)
+                umma_f16(tmem_S, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_qk, k != 0);
+            umma_commit(k_empty);
+            umma_commit(s_full);
+            mbar_wait(p_ready, ph, p.err_flag, 15);
+            mbar_wait(v_full, ph, p.err_flag, 16);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < kBKV / 16; ++k)
+                umma_f16(tmem_O, make_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                         make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, k != 0);
+            umma_commit(v_empty);
+            umma_commit(o_full);
+        }
+    } else if (warp >= 2) {
+        // ---------------- softmax / output (one query row per thread) ----------------
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        float o_acc[kD];
+#pragma unroll
+        for (int i = 0; i < kD; ++i) o_acc[i] = 0.f;
+        const float sc = p.scale_log2;
+        for (int j = 0; j < nkv; ++j) {
+            const uint32_t ph = j & 1;
+            const int kv_valid = min(kBKV, p.Skv - j * kBKV);
+            mbar_wait(s_full, ph, p.err_flag, 17);
+            tc_fence_after();
+            // pass 1: row max
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            const float m_new = fmaxf(m_run, mx * sc);
+            const float alpha = exp2f(m_run - m_new);       // m_run = -inf on the first tile -> 0
+            float psum = 0.f;
+            // pass 2: p = 2^(s*sc - m_new) -> fp16 -> smem (K-major, 128B swizzle: chunk ^= row & 7)
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
+                tmem_ld_wait();
+                uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 pk;
+                    __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int col = c * 32 + g * 8 + 2 * i;
+                        float e0 = (col < kv_valid) ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * i]), sc, -m_new)) : 0.f;
+                        float e1 = (col + 1 < kv_valid) ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * i + 1]), sc, -m_new)) : 0.f;
+                        __half2 h2 = __floats2half2_rn(e0, e1);
+                        // accumulate the row sum from the ROUNDED probabilities (what the PV MMA sees)
+                        float2 back = __half22float2(h2);
+                        psum += back.x + back.y;
+                        ph2[i] = h2;
+                    }
+                    const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
+                    *reinterpret_cast<uint4*>(prow + chunk * 16) = pk;
+                }
+            }
+            l_run = l_run * alpha + psum;
+            m_run = m_new;
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);
+            // O = alpha * O + P V
+            mbar_wait(o_full, ph, p.err_flag, 18);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(v[i]));
+            }
+            tc_fence_before();
+        }
+        const int q = q0 + r;
+        if (q < p.Sq) {
+            const float inv = 1.0f / l_run;
+            __half* dst = p.out + ((long long)b * p.Sq + q) * p.ldo + head * kD;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                uint4 o;
+                __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    oh[i] = __floats2half2_rn(o_acc[g * 8 + 2 * i] * inv, o_acc[g * 8 + 2 * i + 1] * inv);
+                *reinterpret_cast<uint4*>(dst + g * 8) = o;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_rows_map(lb_ctx* ctx, CUtensorMap* m, const void* base, int64_t ld, int64_t cols, int rows, int B) {
+    if (!ctx->tmap_encode) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        LB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
+        LB_REQUIRE(f != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+        ctx->tmap_encode = f;
+    }
+    EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(ctx->tmap_encode);
+    LB_REQUIRE(lb_aligned16(base) && ld % 8 == 0 && cols <= ld, "attention: operand alignment / stride");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * rows};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(attention cols=%lld rows=%d B=%d) failed: %d",
+               (long long)cols, rows, B, (int)r);
+    return 0;
+}
+
+}  // namespace
+
+int* lb_err_flag(lb_ctx* ctx);
+
+struct AttnPlan {
+    AttnParams p;
+    dim3 grid;
+};
+
+int attn_plan_build(lb_ctx* ctx, const lb_attn_desc& d, AttnPlan* plan) {
+    LB_REQUIRE(ctx && plan, "attention: null ctx/plan");
+    LB_REQUIRE(d.q && d.k && d.v && d.out, "attention: null buffer");
+    LB_REQUIRE(d.head_dim == 64, "attention: only head_dim 64 is implemented (got %d)", d.head_dim);
+    LB_REQUIRE(d.B >= 1 && d.heads >= 1 && d.Sq >= 1 && d.Skv >= 1, "attention: bad sizes");
+    LB_REQUIRE(d.out_ld % 8 == 0 && lb_aligned16(d.out), "attention: out alignment");
+    AttnParams& p = plan->p;
+    memset(&p, 0, sizeof(p));
+    const int width = d.heads * 64;
+    if (int e = encode_rows_map(ctx, &p.tmQ, d.q, d.q_ld, d.q_col0 + width, d.Sq, d.B)) return e;
+    if (int e = encode_rows_map(ctx, &p.tmK, d.k, d.k_ld, d.k_col0 + width, d.Skv, d.B)) return e;
+    if (int e = encode_rows_map(ctx, &p.tmV, d.v, d.v_ld, d.v_col0 + width, d.Skv, d.B)) return e;
+    p.Sq = d.Sq; p.Skv = d.Skv; p.heads = d.heads; p.B = d.B;
+    p.q_col0 = d.q_col0; p.k_col0 = d.k_col0; p.v_col0 = d.v_col0;
+    p.out = static_cast<__half*>(d.out);
+    p.ldo = d.out_ld;
+    p.scale_log2 = d.scale * 1.4426950408889634f;
+    p.err_flag = lb_err_flag(ctx);
+    plan->grid = dim3((unsigned)lb_ceil_div(d.Sq, kBQ), (unsigned)d.heads, (unsigned)d.B);
+    return 0;
+}
+
+int attn_plan_launch(const AttnPlan& plan, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        LB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        attr_set = true;
+    }
+    attn_tc_kernel<<<plan.grid, kAttnThreads, kAttnSmem, st>>>(plan.p);
+    LB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lb_attention(lb_ctx* ctx, const lb_attn_desc* desc, void* stream) {
+    LB_REQUIRE(ctx && desc, "lb_attention: null argument");
+    AttnPlan plan;
+    if (int e = attn_plan_build(ctx, *desc, &plan)) return e;
+    return attn_plan_launch(plan, lb_stream(stream));
+}

@@ -117,3 +117,97 @@ def error_flag(dev=0):
     code = ctypes.c_int(0)
     check(_cabi.load().lb_ctx_error_flag(ctx(dev), ctypes.byref(code)), "lb_ctx_error_flag")
     return code.value
+
+
+def attention(q, k, v, out, B, heads, Sq, Skv, q_col0=0, k_col0=0, v_col0=0, scale=0.125):
+    """q/k/v: 2-D row-major fp16 buffers whose column slices hold the heads (lb_attention)."""
+    dev = _dev(q)
+    d = _cabi.AttnDesc()
+    d.q, d.q_ld, d.q_col0 = _p(q), q.stride(0), q_col0
+    d.k, d.k_ld, d.k_col0 = _p(k), k.stride(0), k_col0
+    d.v, d.v_ld, d.v_col0 = _p(v), v.stride(0), v_col0
+    d.out, d.out_ld = _p(out), out.stride(0)
+    d.B, d.heads, d.Sq, d.Skv, d.head_dim, d.scale = B, heads, Sq, Skv, 64, scale
+    check(_cabi.load().lb_attention(ctx(dev), d, stream_ptr()), "lb_attention")
+    return out
+
+
+def groupnorm(x, B, HW, C, groups, gamma, beta, eps, silu, out=None):
+    dev = _dev(x)
+    if out is None:
+        out = torch.empty((B * HW, C), dtype=torch.float16, device=x.device)
+    lib = _cabi.load()
+    ws = _workspace(dev, lib.lb_groupnorm_workspace_bytes(ctx(dev), B, HW, groups))
+    check(lib.lb_groupnorm(ctx(dev), ptr(x), x.stride(0), B, HW, C, groups, ptr(gamma), ptr(beta), float(eps),
+                           int(silu), ptr(out), out.stride(0), ptr(ws), stream_ptr()), "lb_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    dev = _dev(x)
+    rows, C = x.shape
+    if out is None:
+        out = torch.empty((rows, C), dtype=torch.float16, device=x.device)
+    check(_cabi.load().lb_layernorm(ctx(dev), ptr(x), x.stride(0), rows, C, ptr(gamma), ptr(beta), float(eps),
+                                    ptr(out), out.stride(0), stream_ptr()), "lb_layernorm")
+    return out
+
+
+def embed_inputs(t, text_embeds, time_ids, dim_t, dim_a):
+    dev = _dev(text_embeds)
+    B, pooled = text_embeds.shape
+    temb_in = torch.empty((B, dim_t), dtype=torch.float16, device=text_embeds.device)
+    add_in = torch.empty((B, pooled + 6 * dim_a), dtype=torch.float16, device=text_embeds.device)
+    check(_cabi.load().lb_embed_inputs(ctx(dev), float(t), ptr(text_embeds), ptr(time_ids), B, dim_t, pooled, dim_a,
+                                       ptr(temb_in), ptr(add_in), stream_ptr()), "lb_embed_inputs")
+    return temb_in, add_in
+
+
+def linear_small(x, w, bias=None, addend=None, act_in=0, act_out=0, out=None):
+    dev = _dev(x)
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    check(_cabi.load().lb_linear_small(ctx(dev), ptr(x), x.stride(0), M, K, ptr(w), w.stride(0), ptr(bias),
+                                       ptr(addend), 0 if addend is None else addend.stride(0), act_in, act_out,
+                                       ptr(out), out.stride(0), N, stream_ptr()), "lb_linear_small")
+    return out
+
+
+def conv_in(x_nchw, w_packed, bias, Cout, out=None):
+    dev = _dev(x_nchw)
+    B, Cin, H, W = x_nchw.shape
+    if out is None:
+        out = torch.empty((B * H * W, Cout), dtype=torch.float16, device=x_nchw.device)
+    check(_cabi.load().lb_conv_in(ctx(dev), ptr(x_nchw), B, Cin, H, W, ptr(w_packed), ptr(bias), Cout, ptr(out),
+                                  out.stride(0), stream_ptr()), "lb_conv_in")
+    return out
+
+
+def conv_out(x, B, H, W, Cin, w_packed, bias, Cout, out=None):
+    dev = _dev(x)
+    if out is None:
+        out = torch.empty((B, Cout, H, W), dtype=torch.float16, device=x.device)
+    check(_cabi.load().lb_conv_out(ctx(dev), ptr(x), x.stride(0), B, Cin, H, W, ptr(w_packed), ptr(bias), Cout,
+                                   ptr(out), stream_ptr()), "lb_conv_out")
+    return out
+
+
+def upsample2x(x, B, H, W, C, out=None):
+    dev = _dev(x)
+    if out is None:
+        out = torch.empty((B * 4 * H * W, C), dtype=torch.float16, device=x.device)
+    check(_cabi.load().lb_upsample2x(ctx(dev), ptr(x), x.stride(0), B, H, W, C, ptr(out), out.stride(0),
+                                     stream_ptr()), "lb_upsample2x")
+    return out
+
+
+def im2col_s2(x, B, H, W, C, out=None):
+    dev = _dev(x)
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    if out is None:
+        out = torch.empty((B * Ho * Wo, 9 * C), dtype=torch.float16, device=x.device)
+    check(_cabi.load().lb_im2col_s2(ctx(dev), ptr(x), x.stride(0), B, H, W, C, ptr(out), stream_ptr()),
+          "lb_im2col_s2")
+    return out
