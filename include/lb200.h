@@ -170,6 +170,42 @@ int lb_upsample2x(lb_ctx* ctx, const void* x, int64_t ld, int B, int H, int W, i
                   void* stream);
 int lb_im2col_s2(lb_ctx* ctx, const void* x, int64_t ld, int B, int H, int W, int C, void* out, void* stream);
 
+/* ---- UNet executor ---------------------------------------------------------------
+ * A program is a flat list of the ops above over static device buffers (one
+ * SDXL UNet forward for a fixed batch/height/width lowers to ~1.7k records).
+ * lb_program_create validates every record and pre-encodes the TMA descriptors;
+ * lb_program_run replays it on ``stream`` (``t`` = the timestep fed to
+ * LB_OP_EMBED_INPUTS).  Replaces the module walk of pipe.unet(...)
+ * (diffusers_holder.py:336-344).
+ */
+enum {
+    LB_OP_GEMM = 1, LB_OP_ATTENTION = 2, LB_OP_GROUPNORM = 3, LB_OP_LAYERNORM = 4, LB_OP_EMBED_INPUTS = 5,
+    LB_OP_LINEAR_SMALL = 6, LB_OP_CONV_IN = 7, LB_OP_CONV_OUT = 8, LB_OP_UPSAMPLE2X = 9, LB_OP_IM2COL_S2 = 10
+};
+typedef struct lb_op {
+    int32_t kind;
+    int32_t reserved;
+    union {
+        lb_gemm_desc gemm;
+        lb_attn_desc attn;
+        struct { const void* x; int64_t ld_x; int64_t rows; /* HW per batch (GN) or total rows (LN) */
+                 int32_t B, C, groups, silu; float eps; const void* gamma; const void* beta;
+                 void* out; int64_t ld_out; void* workspace; } norm;
+        struct { const void* text_embeds; const void* time_ids; int32_t B, dim_t, pooled, dim_a;
+                 void* temb_in; void* add_in; } embed;
+        struct { const void* x; int64_t ldx; int32_t M, K; const void* w; int64_t ldw; const void* bias;
+                 const void* addend; int64_t ldadd; int32_t act_in, act_out; void* out; int64_t ldo; int32_t N; } lin;
+        struct { const void* x; int64_t ld_x; int32_t B, Cin, H, W; const void* w; const void* bias;
+                 int32_t Cout; void* out; int64_t ld_out; } conv;
+        struct { const void* x; int64_t ld_x; int32_t B, H, W, C; void* out; int64_t ld_out; } resample;
+    } u;
+} lb_op;
+typedef struct lb_program lb_program;
+int     lb_program_create(lb_ctx* ctx, const lb_op* ops, int64_t n_ops, lb_program** out);
+int     lb_program_run(lb_program* prog, float t, void* stream);
+int64_t lb_program_num_launches(lb_program* prog);
+int     lb_program_destroy(lb_program* prog);
+
 /* Reads and clears the device-side protocol-error flag the pipelined kernels
  * set before trapping (0 = no error).  Synchronises the device: debug only. */
 int lb_ctx_error_flag(lb_ctx* ctx, int* out_code);

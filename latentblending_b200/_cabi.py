@@ -40,6 +40,50 @@ class AttnDesc(ctypes.Structure):
                 ("head_dim", ctypes.c_int32), ("scale", c_float)]
 
 
+c_int32 = ctypes.c_int32
+
+
+class _NormOp(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("ld_x", c_int64), ("rows", c_int64), ("B", c_int32), ("C", c_int32),
+                ("groups", c_int32), ("silu", c_int32), ("eps", c_float), ("gamma", c_void_p), ("beta", c_void_p),
+                ("out", c_void_p), ("ld_out", c_int64), ("workspace", c_void_p)]
+
+
+class _EmbedOp(ctypes.Structure):
+    _fields_ = [("text_embeds", c_void_p), ("time_ids", c_void_p), ("B", c_int32), ("dim_t", c_int32),
+                ("pooled", c_int32), ("dim_a", c_int32), ("temb_in", c_void_p), ("add_in", c_void_p)]
+
+
+class _LinOp(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("ldx", c_int64), ("M", c_int32), ("K", c_int32), ("w", c_void_p), ("ldw", c_int64),
+                ("bias", c_void_p), ("addend", c_void_p), ("ldadd", c_int64), ("act_in", c_int32),
+                ("act_out", c_int32), ("out", c_void_p), ("ldo", c_int64), ("N", c_int32)]
+
+
+class _ConvOp(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("ld_x", c_int64), ("B", c_int32), ("Cin", c_int32), ("H", c_int32), ("W", c_int32),
+                ("w", c_void_p), ("bias", c_void_p), ("Cout", c_int32), ("out", c_void_p), ("ld_out", c_int64)]
+
+
+class _ResampleOp(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("ld_x", c_int64), ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32),
+                ("out", c_void_p), ("ld_out", c_int64)]
+
+
+class _OpUnion(ctypes.Union):
+    _fields_ = [("gemm", GemmDesc), ("attn", AttnDesc), ("norm", _NormOp), ("embed", _EmbedOp), ("lin", _LinOp),
+                ("conv", _ConvOp), ("resample", _ResampleOp)]
+
+
+class Op(ctypes.Structure):
+    """lb_op of include/lb200.h."""
+    _fields_ = [("kind", c_int32), ("reserved", c_int32), ("u", _OpUnion)]
+
+
+(OP_GEMM, OP_ATTENTION, OP_GROUPNORM, OP_LAYERNORM, OP_EMBED_INPUTS, OP_LINEAR_SMALL, OP_CONV_IN, OP_CONV_OUT,
+ OP_UPSAMPLE2X, OP_IM2COL_S2) = range(1, 11)
+
+
 # name -> (restype, argtypes); mirrors include/lb200.h one to one
 SIGNATURES = {
     "lb_abi_version": (c_int, []),
@@ -56,6 +100,10 @@ SIGNATURES = {
                                   c_float, c_float, c_float, c_float, c_void_p]),
     "lb_gemm": (c_int, [c_void_p, ctypes.POINTER(GemmDesc), c_void_p]),
     "lb_ctx_error_flag": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
+    "lb_program_create": (c_int, [c_void_p, ctypes.POINTER(Op), c_int64, ctypes.POINTER(c_void_p)]),
+    "lb_program_run": (c_int, [c_void_p, c_float, c_void_p]),
+    "lb_program_num_launches": (c_int64, [c_void_p]),
+    "lb_program_destroy": (c_int, [c_void_p]),
     "lb_attention": (c_int, [c_void_p, ctypes.POINTER(AttnDesc), c_void_p]),
     "lb_groupnorm_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "lb_groupnorm": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,

@@ -288,3 +288,16 @@ extern "C" int lb_attention(lb_ctx* ctx, const lb_attn_desc* desc, void* stream)
     if (int e = attn_plan_build(ctx, *desc, &plan)) return e;
     return attn_plan_launch(plan, lb_stream(stream));
 }
+
+// opaque handles for program.cu (AttnPlan holds CUtensorMaps and needs 64-byte alignment)
+int attn_plan_build_opaque(lb_ctx* ctx, const lb_attn_desc& d, void** plan_out) {
+    AttnPlan* plan = new AttnPlan();
+    if (int e = attn_plan_build(ctx, d, plan)) {
+        delete plan;
+        return e;
+    }
+    *plan_out = plan;
+    return 0;
+}
+int attn_plan_launch_opaque(void* plan, cudaStream_t st) { return attn_plan_launch(*static_cast<AttnPlan*>(plan), st); }
+void attn_plan_free_opaque(void* plan) { delete static_cast<AttnPlan*>(plan); }

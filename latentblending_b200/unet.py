@@ -1,0 +1,500 @@
+"""SDXL UNet on liblb200: weight packing + lowering of one forward pass to a C-ABI program.
+
+Host side of the executor that replaces ``pipe.unet(...)`` in the reference's
+denoise loop (latentblending/diffusers_holder.py:336-344).  Parameters are taken
+by their diffusers ``state_dict`` names, so ``pipe.unet.state_dict()`` of a real
+StableDiffusionXLPipeline can be passed as is.
+
+Data layout in HBM (all fp16):
+  * activations NHWC, i.e. [B*H*W, C] row-major with an explicit row stride so
+    that channel slices of a wider buffer are first-class tensors; the nine
+    ``torch.cat([hidden, skip])`` of the up path are never materialised: every
+    skip tensor is written by its producer straight into the right half of its
+    future concat buffer and read from there by the down path;
+  * weights [N, K] row-major (K-major for the tensor core B operand); 3x3 conv
+    weights [Cout][ky][kx][Cin]; a resnet's 1x1 shortcut is appended along K of
+    conv2 (one accumulator, biases pre-summed); to_q/to_k/to_v fused to one
+    [3C, C] matrix, cross-attention to_k/to_v to [2C, ctx]; GEGLU rows
+    interleaved per 128-row tile (64 value rows then their 64 gate rows);
+    all resnet ``time_emb_proj`` stacked into one [sum Cout, T] matrix.
+  * latents / eps stay NCHW [B,4,h,w] like the reference's tensors.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import (OP_ATTENTION, OP_CONV_IN, OP_CONV_OUT, OP_EMBED_INPUTS, OP_GEMM, OP_GROUPNORM, OP_IM2COL_S2,
+                    OP_LAYERNORM, OP_LINEAR_SMALL, OP_UPSAMPLE2X, Op, check, ctx, stream_ptr)
+
+
+@dataclass
+class UNetConfig:
+    in_channels: int = 4
+    out_channels: int = 4
+    block_out_channels: Tuple[int, ...] = (320, 640, 1280)
+    layers_per_block: int = 2
+    transformer_layers: Tuple[int, ...] = (0, 2, 10)
+    head_dim: int = 64
+    cross_attention_dim: int = 2048
+    addition_time_embed_dim: int = 256
+    pooled_dim: int = 1280
+    norm_num_groups: int = 32
+    sample_size: int = 128
+    time_cond_proj_dim: object = None
+
+    @property
+    def time_embed_dim(self):
+        return self.block_out_channels[0] * 4
+
+    @property
+    def add_in_dim(self):
+        return self.pooled_dim + 6 * self.addition_time_embed_dim
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class Program:
+    """A recorded op list; ``finalize`` hands it to lb_program_create."""
+
+    def __init__(self, device_index):
+        self.dev = device_index
+        self.ops = []
+        self.keep = []          # tensors referenced by raw pointers must outlive the program
+        self.handle = None
+
+    def _new(self, kind):
+        op = Op()
+        op.kind = kind
+        self.ops.append(op)
+        return op
+
+    def hold(self, *ts):
+        self.keep.extend(t for t in ts if t is not None)
+
+    # -- op emitters (mirror latentblending_b200.ops, but record instead of launching) --------
+    def gemm(self, a0, w, N, B, H, W, out, taps=1, a0_c=None, a1=None, a1_c=None, bias=None, bias2=None, res=None,
+             mode=0):
+        d = self._new(OP_GEMM).u.gemm
+        d.a0, d.a0_ld, d.a0_c = _p(a0), a0.stride(0), (a0.shape[1] if a0_c is None else a0_c)
+        if a1 is not None:
+            d.a1, d.a1_ld, d.a1_c = _p(a1), a1.stride(0), (a1.shape[1] if a1_c is None else a1_c)
+        d.B, d.H, d.W, d.taps = B, H, W, taps
+        d.w, d.w_ld, d.N = _p(w), w.stride(0), N
+        d.bias = _p(bias)
+        if bias2 is not None:
+            d.bias2, d.bias2_ld = _p(bias2), bias2.stride(0)
+        if res is not None:
+            d.res, d.res_ld = _p(res), res.stride(0)
+        d.out, d.out_ld, d.mode = _p(out), out.stride(0), mode
+        self.hold(a0, w, a1, bias, bias2, res, out)
+
+    def attention(self, q, k, v, out, B, heads, Sq, Skv, q_col0=0, k_col0=0, v_col0=0, scale=0.125):
+        d = self._new(OP_ATTENTION).u.attn
+        d.q, d.q_ld, d.q_col0 = _p(q), q.stride(0), q_col0
+        d.k, d.k_ld, d.k_col0 = _p(k), k.stride(0), k_col0
+        d.v, d.v_ld, d.v_col0 = _p(v), v.stride(0), v_col0
+        d.out, d.out_ld = _p(out), out.stride(0)
+        d.B, d.heads, d.Sq, d.Skv, d.head_dim, d.scale = B, heads, Sq, Skv, 64, scale
+        self.hold(q, k, v, out)
+
+    def groupnorm(self, x, B, HW, C, groups, gamma, beta, eps, silu, out, ws):
+        d = self._new(OP_GROUPNORM).u.norm
+        d.x, d.ld_x, d.rows, d.B, d.C, d.groups, d.silu, d.eps = _p(x), x.stride(0), HW, B, C, groups, int(silu), eps
+        d.gamma, d.beta, d.out, d.ld_out, d.workspace = _p(gamma), _p(beta), _p(out), out.stride(0), _p(ws)
+        self.hold(x, gamma, beta, out, ws)
+
+    def layernorm(self, x, gamma, beta, eps, out):
+        d = self._new(OP_LAYERNORM).u.norm
+        d.x, d.ld_x, d.rows, d.B, d.C, d.eps = _p(x), x.stride(0), x.shape[0], 1, x.shape[1], eps
+        d.gamma, d.beta, d.out, d.ld_out = _p(gamma), _p(beta), _p(out), out.stride(0)
+        self.hold(x, gamma, beta, out)
+
+    def embed_inputs(self, text_embeds, time_ids, dim_t, dim_a, temb_in, add_in):
+        d = self._new(OP_EMBED_INPUTS).u.embed
+        d.text_embeds, d.time_ids = _p(text_embeds), _p(time_ids)
+        d.B, d.dim_t, d.pooled, d.dim_a = text_embeds.shape[0], dim_t, text_embeds.shape[1], dim_a
+        d.temb_in, d.add_in = _p(temb_in), _p(add_in)
+        self.hold(text_embeds, time_ids, temb_in, add_in)
+
+    def linear_small(self, x, w, out, bias=None, addend=None, act_in=0, act_out=0):
+        d = self._new(OP_LINEAR_SMALL).u.lin
+        d.x, d.ldx, d.M, d.K = _p(x), x.stride(0), x.shape[0], x.shape[1]
+        d.w, d.ldw, d.bias = _p(w), w.stride(0), _p(bias)
+        if addend is not None:
+            d.addend, d.ldadd = _p(addend), addend.stride(0)
+        d.act_in, d.act_out, d.out, d.ldo, d.N = act_in, act_out, _p(out), out.stride(0), w.shape[0]
+        self.hold(x, w, out, bias, addend)
+
+    def conv_in(self, x_nchw, w, bias, Cout, out):
+        d = self._new(OP_CONV_IN).u.conv
+        B, Cin, H, W = x_nchw.shape
+        d.x, d.B, d.Cin, d.H, d.W, d.w, d.bias, d.Cout = _p(x_nchw), B, Cin, H, W, _p(w), _p(bias), Cout
+        d.out, d.ld_out = _p(out), out.stride(0)
+        self.hold(x_nchw, w, bias, out)
+
+    def conv_out(self, x, B, H, W, Cin, w, bias, Cout, out_nchw):
+        d = self._new(OP_CONV_OUT).u.conv
+        d.x, d.ld_x, d.B, d.Cin, d.H, d.W = _p(x), x.stride(0), B, Cin, H, W
+        d.w, d.bias, d.Cout, d.out = _p(w), _p(bias), Cout, _p(out_nchw)
+        self.hold(x, w, bias, out_nchw)
+
+    def upsample2x(self, x, B, H, W, C, out):
+        d = self._new(OP_UPSAMPLE2X).u.resample
+        d.x, d.ld_x, d.B, d.H, d.W, d.C, d.out, d.ld_out = _p(x), x.stride(0), B, H, W, C, _p(out), out.stride(0)
+        self.hold(x, out)
+
+    def im2col_s2(self, x, B, H, W, C, out):
+        d = self._new(OP_IM2COL_S2).u.resample
+        d.x, d.ld_x, d.B, d.H, d.W, d.C, d.out, d.ld_out = _p(x), x.stride(0), B, H, W, C, _p(out), out.stride(0)
+        self.hold(x, out)
+
+    # -- lifecycle --------------------------------------------------------------------------
+    def finalize(self):
+        arr = (Op * len(self.ops))(*self.ops)
+        h = ctypes.c_void_p()
+        check(_cabi.load().lb_program_create(ctx(self.dev), arr, len(self.ops), ctypes.byref(h)), "lb_program_create")
+        self.handle = h
+        self.num_launches = int(_cabi.load().lb_program_num_launches(h))
+        return self
+
+    def run(self, t=0.0):
+        check(_cabi.load().lb_program_run(self.handle, float(t), stream_ptr()), "lb_program_run")
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                _cabi.load().lb_program_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def _geglu_perm(inner, device):
+    idx = torch.arange(inner, device=device).view(-1, 64)
+    return torch.stack([idx, idx + inner], dim=1).reshape(-1)
+
+
+class PackedUNet:
+    """fp16 device copies of the UNet parameters in the layouts the kernels consume."""
+
+    def __init__(self, cfg: UNetConfig, state_dict, device):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        sd = state_dict
+        dev = self.device
+
+        def g(name):
+            return sd[name].detach().to(device=dev, dtype=torch.float16).contiguous()
+
+        def conv3(name):      # [Cout,Cin,3,3] -> [Cout][ky][kx][Cin]
+            w = g(name + ".weight")
+            return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+        self.g = g
+        self.w = {}
+        W = self.w
+        W["conv_in.w"] = g("conv_in.weight").permute(2, 3, 1, 0).contiguous()      # [ky][kx][cin][Cout]
+        W["conv_in.b"] = g("conv_in.bias")
+        W["conv_out.w"] = g("conv_out.weight").permute(0, 2, 3, 1).contiguous()     # [co][ky][kx][Cin]
+        W["conv_out.b"] = g("conv_out.bias")
+        for nm in ("conv_norm_out",):
+            W[nm + ".g"], W[nm + ".b"] = g(nm + ".weight"), g(nm + ".bias")
+        for e in ("time_embedding", "add_embedding"):
+            for l in ("linear_1", "linear_2"):
+                W[f"{e}.{l}.w"], W[f"{e}.{l}.b"] = g(f"{e}.{l}.weight"), g(f"{e}.{l}.bias")
+        # resnets (names collected in forward order so the stacked time_emb_proj offsets line up)
+        self.resnet_names = [k[: -len(".norm1.weight")] for k in sd if k.endswith(".norm1.weight") and "resnets" in k]
+        temb_w, temb_b, off = [], [], 0
+        self.temb_off = {}
+        for r in self.resnet_names:
+            W[r + ".norm1.g"], W[r + ".norm1.b"] = g(r + ".norm1.weight"), g(r + ".norm1.bias")
+            W[r + ".norm2.g"], W[r + ".norm2.b"] = g(r + ".norm2.weight"), g(r + ".norm2.bias")
+            W[r + ".conv1.w"], W[r + ".conv1.b"] = conv3(r + ".conv1"), g(r + ".conv1.bias")
+            w2, b2 = conv3(r + ".conv2"), g(r + ".conv2.bias")
+            if (r + ".conv_shortcut.weight") in sd:
+                ws = g(r + ".conv_shortcut.weight")
+                w2 = torch.cat([w2, ws.reshape(ws.shape[0], -1)], dim=1).contiguous()
+                b2 = (b2.float() + g(r + ".conv_shortcut.bias").float()).half()
+                W[r + ".has_shortcut"] = True
+            W[r + ".conv2.w"], W[r + ".conv2.b"] = w2, b2
+            tw, tb = g(r + ".time_emb_proj.weight"), g(r + ".time_emb_proj.bias")
+            self.temb_off[r] = (off, tw.shape[0])
+            off += tw.shape[0]
+            temb_w.append(tw)
+            temb_b.append(tb)
+        W["temb_all.w"], W["temb_all.b"] = torch.cat(temb_w, 0).contiguous(), torch.cat(temb_b, 0).contiguous()
+        self.temb_total = off
+        # transformers
+        self.tf_names = [k[: -len(".proj_in.weight")] for k in sd if k.endswith(".proj_in.weight")]
+        for a in self.tf_names:
+            W[a + ".norm.g"], W[a + ".norm.b"] = g(a + ".norm.weight"), g(a + ".norm.bias")
+            W[a + ".proj_in.w"], W[a + ".proj_in.b"] = g(a + ".proj_in.weight"), g(a + ".proj_in.bias")
+            W[a + ".proj_out.w"], W[a + ".proj_out.b"] = g(a + ".proj_out.weight"), g(a + ".proj_out.bias")
+            depth = 0
+            while f"{a}.transformer_blocks.{depth}.norm1.weight" in sd:
+                t = f"{a}.transformer_blocks.{depth}"
+                for n in ("norm1", "norm2", "norm3"):
+                    W[f"{t}.{n}.g"], W[f"{t}.{n}.b"] = g(f"{t}.{n}.weight"), g(f"{t}.{n}.bias")
+                W[t + ".attn1.qkv.w"] = torch.cat([g(t + ".attn1.to_q.weight"), g(t + ".attn1.to_k.weight"),
+                                                    g(t + ".attn1.to_v.weight")], 0).contiguous()
+                W[t + ".attn1.out.w"], W[t + ".attn1.out.b"] = g(t + ".attn1.to_out.0.weight"), g(t + ".attn1.to_out.0.bias")
+                W[t + ".attn2.q.w"] = g(t + ".attn2.to_q.weight")
+                W[t + ".attn2.kv.w"] = torch.cat([g(t + ".attn2.to_k.weight"), g(t + ".attn2.to_v.weight")], 0).contiguous()
+                W[t + ".attn2.out.w"], W[t + ".attn2.out.b"] = g(t + ".attn2.to_out.0.weight"), g(t + ".attn2.to_out.0.bias")
+                pw, pb = g(t + ".ff.net.0.proj.weight"), g(t + ".ff.net.0.proj.bias")
+                perm = _geglu_perm(pw.shape[0] // 2, dev)
+                W[t + ".ff.in.w"], W[t + ".ff.in.b"] = pw[perm].contiguous(), pb[perm].contiguous()
+                W[t + ".ff.out.w"], W[t + ".ff.out.b"] = g(t + ".ff.net.2.weight"), g(t + ".ff.net.2.bias")
+                depth += 1
+            W[a + ".depth"] = depth
+        for k in sd:
+            if k.endswith("samplers.0.conv.weight"):
+                nm = k[: -len(".weight")]
+                W[nm + ".w"], W[nm + ".b"] = conv3(nm), g(nm + ".bias")
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.w.values() if torch.is_tensor(t))
+
+
+class UNetB200:
+    """One lowered forward per (batch, h, w); ``forward`` replays it."""
+
+    def __init__(self, cfg: UNetConfig, state_dict, device="cuda:0"):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.dev_index = self.device.index or 0
+        self.packed = PackedUNet(cfg, state_dict, self.device)
+        self._plans = {}
+
+    # -- public -----------------------------------------------------------------------------
+    def plan(self, B, H, W):
+        key = (B, H, W)
+        if key not in self._plans:
+            self._plans[key] = _Lowering(self, B, H, W)
+        return self._plans[key]
+
+    @torch.no_grad()
+    def forward(self, x, t, encoder_hidden_states, text_embeds, time_ids, ctx_changed=True):
+        """x [B,4,h,w] fp16 NCHW -> eps [B,4,h,w] fp16 (a view of the plan's static output buffer)."""
+        B, _, H, W = x.shape
+        pl = self.plan(B, H, W)
+        pl.x_in.copy_(x)
+        pl.text.copy_(text_embeds)
+        pl.tids.copy_(time_ids)
+        if ctx_changed:
+            pl.ctx.copy_(encoder_hidden_states.reshape(pl.ctx.shape))
+            pl.prog_ctx.run()
+        pl.prog_step.run(float(t))
+        return pl.eps
+
+    def launches_per_forward(self, B, H, W):
+        pl = self.plan(B, H, W)
+        return pl.prog_step.num_launches, pl.prog_ctx.num_launches
+
+
+class _Lowering:
+    def __init__(self, net: UNetB200, B, H, W):
+        cfg, Wt = net.cfg, net.packed.w
+        self.net, self.B, self.H, self.W = net, B, H, W
+        dev = net.device
+        f16 = dict(dtype=torch.float16, device=dev)
+        ch = list(cfg.block_out_channels)
+        L = len(ch)
+        assert H % (1 << (L - 1)) == 0 and W % (1 << (L - 1)) == 0, "latent size must be divisible by 2^(levels-1)"
+        T = cfg.time_embed_dim
+        groups = cfg.norm_num_groups
+        self.x_in = torch.zeros(B, cfg.in_channels, H, W, **f16)
+        self.eps = torch.zeros(B, cfg.out_channels, H, W, **f16)
+        self.ctx = torch.zeros(B * 77, cfg.cross_attention_dim, **f16)
+        self.text = torch.zeros(B, cfg.pooled_dim, **f16)
+        self.tids = torch.zeros(B, 6, **f16)
+        self.ws = torch.zeros(max(1 << 16, _cabi.load().lb_groupnorm_workspace_bytes(ctx(net.dev_index), B, H * W, groups)),
+                              dtype=torch.uint8, device=dev)
+        P = self.prog_step = Program(net.dev_index)
+        PC = self.prog_ctx = Program(net.dev_index)
+        self._scratch = {}
+
+        def scratch(name, rows, cols):
+            key = name
+            need = rows * cols
+            buf = self._scratch.get(key)
+            if buf is None or buf.numel() < need:
+                buf = torch.empty(need, **f16)
+                self._scratch[key] = buf
+            return buf[:need].view(rows, cols)
+
+        self._persist = []
+
+        def persist(rows, cols):
+            t = torch.empty(rows, cols, **f16)
+            self._persist.append(t)
+            return t
+
+        # ---- embeddings -------------------------------------------------------------------
+        temb_in, add_in = persist(B, ch[0]), persist(B, cfg.add_in_dim)
+        P.embed_inputs(self.text, self.tids, ch[0], cfg.addition_time_embed_dim, temb_in, add_in)
+        t1, a1, temb, emb = persist(B, T), persist(B, T), persist(B, T), persist(B, T)
+        P.linear_small(temb_in, Wt["time_embedding.linear_1.w"], t1, bias=Wt["time_embedding.linear_1.b"], act_out=1)
+        P.linear_small(t1, Wt["time_embedding.linear_2.w"], temb, bias=Wt["time_embedding.linear_2.b"])
+        P.linear_small(add_in, Wt["add_embedding.linear_1.w"], a1, bias=Wt["add_embedding.linear_1.b"], act_out=1)
+        P.linear_small(a1, Wt["add_embedding.linear_2.w"], emb, bias=Wt["add_embedding.linear_2.b"], addend=temb)
+        temb_all = persist(B, net.packed.temb_total)
+        P.linear_small(emb, Wt["temb_all.w"], temb_all, bias=Wt["temb_all.b"], act_in=1)
+
+        # ---- geometry + concat buffers ------------------------------------------------------
+        res_hw = [(H >> i, W >> i) for i in range(L)]
+
+        def rows_at(level):
+            return B * res_hw[level][0] * res_hw[level][1]
+
+        # skip list: (level, channels) in production order
+        skip_meta = [(0, ch[0])]
+        for i in range(L):
+            skip_meta += [(i, ch[i])] * cfg.layers_per_block
+            if i < L - 1:
+                skip_meta.append((i + 1, ch[i]))
+        # up path consumption: resnet j of up block i
+        rev = list(reversed(ch))
+        cats = []              # in pop order
+        cprev = rev[0]
+        k = len(skip_meta) - 1
+        for i in range(L):
+            cout = rev[i]
+            for j in range(cfg.layers_per_block + 1):
+                hidden_c = cprev if j == 0 else cout
+                lvl, sc = skip_meta[k]
+                buf = persist(rows_at(lvl), hidden_c + sc)
+                cats.append(dict(buf=buf, hidden=buf[:, :hidden_c], skip=buf[:, hidden_c:], level=lvl))
+                k -= 1
+            cprev = cout
+        skip_views = [c["skip"] for c in reversed(cats)]      # index by production order
+
+        def tslice(rname):
+            off, n = net.packed.temb_off[rname]
+            return temb_all[:, off:off + n]
+
+        def resnet(rname, x, cin, cout, level, out):
+            h_, w_ = res_hw[level]
+            M = rows_at(level)
+            n1 = scratch("n1", M, cin)
+            P.groupnorm(x, B, h_ * w_, cin, groups, Wt[rname + ".norm1.g"], Wt[rname + ".norm1.b"], 1e-5, 1, n1, self.ws)
+            h1 = scratch("h1", M, cout)
+            P.gemm(n1, Wt[rname + ".conv1.w"], cout, B, h_, w_, h1, taps=9, bias=Wt[rname + ".conv1.b"], bias2=tslice(rname))
+            n2 = scratch("n2", M, cout)
+            P.groupnorm(h1, B, h_ * w_, cout, groups, Wt[rname + ".norm2.g"], Wt[rname + ".norm2.b"], 1e-5, 1, n2, self.ws)
+            if Wt.get(rname + ".has_shortcut"):
+                P.gemm(n2, Wt[rname + ".conv2.w"], cout, B, h_, w_, out, taps=9, a1=x, a1_c=cin, bias=Wt[rname + ".conv2.b"])
+            else:
+                P.gemm(n2, Wt[rname + ".conv2.w"], cout, B, h_, w_, out, taps=9, bias=Wt[rname + ".conv2.b"], res=x)
+
+        kv_cache = {}
+
+        def transformer(aname, x, C, level, out):
+            h_, w_ = res_hw[level]
+            S = h_ * w_
+            M = rows_at(level)
+            heads = C // cfg.head_dim
+            tn = scratch("tn", M, C)
+            P.groupnorm(x, B, S, C, groups, Wt[aname + ".norm.g"], Wt[aname + ".norm.b"], 1e-6, 0, tn, self.ws)
+            hs = scratch("hs", M, C)
+            P.gemm(tn, Wt[aname + ".proj_in.w"], C, 1, 1, M, hs, bias=Wt[aname + ".proj_in.b"])
+            for d in range(Wt[aname + ".depth"]):
+                t = f"{aname}.transformer_blocks.{d}"
+                ln = scratch("ln", M, C)
+                P.layernorm(hs, Wt[t + ".norm1.g"], Wt[t + ".norm1.b"], 1e-5, ln)
+                qkv = scratch("qkv", M, 3 * C)
+                P.gemm(ln, Wt[t + ".attn1.qkv.w"], 3 * C, 1, 1, M, qkv)
+                att = scratch("att", M, C)
+                P.attention(qkv, qkv, qkv, att, B, heads, S, S, 0, C, 2 * C, cfg.head_dim ** -0.5)
+                P.gemm(att, Wt[t + ".attn1.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".attn1.out.b"], res=hs)
+                P.layernorm(hs, Wt[t + ".norm2.g"], Wt[t + ".norm2.b"], 1e-5, ln)
+                q = scratch("q", M, C)
+                P.gemm(ln, Wt[t + ".attn2.q.w"], C, 1, 1, M, q)
+                kv = persist(B * 77, 2 * C)         # depends on the conditioning only: computed by prog_ctx
+                PC.gemm(self.ctx, Wt[t + ".attn2.kv.w"], 2 * C, 1, 1, B * 77, kv)
+                kv_cache[t] = kv
+                P.attention(q, kv, kv, att, B, heads, S, 77, 0, 0, C, cfg.head_dim ** -0.5)
+                P.gemm(att, Wt[t + ".attn2.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".attn2.out.b"], res=hs)
+                P.layernorm(hs, Wt[t + ".norm3.g"], Wt[t + ".norm3.b"], 1e-5, ln)
+                gg = scratch("geglu", M, 4 * C)
+                P.gemm(ln, Wt[t + ".ff.in.w"], 8 * C, 1, 1, M, gg, bias=Wt[t + ".ff.in.b"], mode=1)
+                P.gemm(gg, Wt[t + ".ff.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".ff.out.b"], res=hs)
+            P.gemm(hs, Wt[aname + ".proj_out.w"], C, 1, 1, M, out, bias=Wt[aname + ".proj_out.b"], res=x)
+
+        # ---- down path ----------------------------------------------------------------------
+        si = 0
+        P.conv_in(self.x_in, Wt["conv_in.w"], Wt["conv_in.b"], ch[0], skip_views[si])
+        x, cin = skip_views[si], ch[0]
+        si += 1
+        for i in range(L):
+            cout = ch[i]
+            for j in range(cfg.layers_per_block):
+                rname = f"down_blocks.{i}.resnets.{j}"
+                dst = skip_views[si]
+                if cfg.transformer_layers[i]:
+                    r_out = persist(rows_at(i), cout)
+                    resnet(rname, x, cin, cout, i, r_out)
+                    transformer(f"down_blocks.{i}.attentions.{j}", r_out, cout, i, dst)
+                else:
+                    resnet(rname, x, cin, cout, i, dst)
+                x, cin = dst, cout
+                si += 1
+            if i < L - 1:
+                nm = f"down_blocks.{i}.downsamplers.0.conv"
+                h_, w_ = res_hw[i]
+                cols = scratch("im2col", rows_at(i + 1), 9 * cout)
+                P.im2col_s2(x, B, h_, w_, cout, cols)
+                dst = skip_views[si]
+                P.gemm(cols, Wt[nm + ".w"], cout, 1, 1, rows_at(i + 1), dst, bias=Wt[nm + ".b"])
+                x = dst
+                si += 1
+        # ---- mid ----------------------------------------------------------------------------
+        lv, cm = L - 1, ch[-1]
+        m1 = persist(rows_at(lv), cm)
+        resnet("mid_block.resnets.0", x, cm, cm, lv, m1)
+        m2 = persist(rows_at(lv), cm)
+        transformer("mid_block.attentions.0", m1, cm, lv, m2)
+        resnet("mid_block.resnets.1", m2, cm, cm, lv, cats[0]["hidden"])
+        # ---- up path ------------------------------------------------------------------------
+        ci = 0
+        rev_depth = list(reversed(cfg.transformer_layers))
+        for i in range(L):
+            cout = rev[i]
+            lvl = L - 1 - i
+            n_res = cfg.layers_per_block + 1
+            for j in range(n_res):
+                cat = cats[ci]
+                cin_total = cat["buf"].shape[1]
+                last_of_block = j == n_res - 1
+                last_overall = last_of_block and i == L - 1
+                if last_overall:
+                    dst = persist(rows_at(lvl), cout)
+                elif last_of_block:
+                    dst = persist(rows_at(lvl), cout)          # goes through the upsampler
+                else:
+                    dst = cats[ci + 1]["hidden"]
+                rname = f"up_blocks.{i}.resnets.{j}"
+                if rev_depth[i]:
+                    r_out = persist(rows_at(lvl), cout)
+                    resnet(rname, cat["buf"], cin_total, cout, lvl, r_out)
+                    transformer(f"up_blocks.{i}.attentions.{j}", r_out, cout, lvl, dst)
+                else:
+                    resnet(rname, cat["buf"], cin_total, cout, lvl, dst)
+                ci += 1
+                x = dst
+            if i < L - 1:
+                nm = f"up_blocks.{i}.upsamplers.0.conv"
+                h_, w_ = res_hw[lvl]
+                up = scratch("up", rows_at(lvl - 1), cout)
+                P.upsample2x(x, B, h_, w_, cout, up)
+                P.gemm(up, Wt[nm + ".w"], cout, B, 2 * h_, 2 * w_, cats[ci]["hidden"], taps=9, bias=Wt[nm + ".b"])
+        # ---- out ----------------------------------------------------------------------------
+        no = scratch("n1", rows_at(0), ch[0])
+        P.groupnorm(x, B, H * W, ch[0], groups, Wt["conv_norm_out.g"], Wt["conv_norm_out.b"], 1e-5, 1, no, self.ws)
+        P.conv_out(no, B, H, W, ch[0], Wt["conv_out.w"], Wt["conv_out.b"], cfg.out_channels, self.eps)
+        P.finalize()
+        PC.finalize()
