@@ -339,7 +339,7 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
     memset(&p, 0, sizeof(p));
     // --- M tiling: a 128-row tile is a (tw x th x tb) box of pixels
     int tw, th, tb;
-    if (d.W >= kBM) {
+    if (d.W >= kBM || (d.H == 1 && d.B == 1)) {   // rows of a plain matrix: ragged tail is zero-filled by TMA
         tw = kBM; th = 1; tb = 1;
     } else {
         LB_REQUIRE(is_pow2(d.W), "gemm: W (%d) < 128 must be a power of two", d.W);

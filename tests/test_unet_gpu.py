@@ -37,6 +37,7 @@ def _run_pair(ocfg, B, h, w, t, seed=0):
     from latentblending_b200 import ops
     assert ops.error_flag() == 0
     rel = ((eps - ref).norm() / ref.norm()).item()
+    print(f"unet parity: B={B} h={h} w={w} t={t} rel_l2={rel:.3e}")
     return rel, eps, ref, net
 
 
@@ -69,4 +70,4 @@ def test_full_sdxl_unet_matches_oracle_at_256px():
     rel, eps, ref, net = _run_pair(SDXL_BASE, 2, 32, 32, 925.0)
     assert torch.isfinite(eps).all()
     assert rel <= 5e-3, f"relative L2 error {rel}"
-    assert net.launches_per_forward(2, 32, 32)[0] > 1000
+    assert net.launches_per_forward(2, 32, 32)[0] > 900
