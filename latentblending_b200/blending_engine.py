@@ -1,0 +1,483 @@
+"""BlendingEngine: drop-in for latentblending.BlendingEngine on the B200 backend.
+
+Public surface, defaults and quirks follow latentblending/blending_engine.py
+(:20-96 constructor, :120-293 setters, :295-365 run_transition, :370-465
+compute_latents1/2/_mix, :467-529 get_time_based_branching, :531-588 tree
+placement, :643-654 mixed conditioning, :669-742 writers / swap_forward).
+
+What is different underneath (B200-first, same results):
+  * the parental mix of a branch (30 per-step slerps in the reference, :442-450)
+    is one batched lb_slerp_rows launch over the parents' contiguous trajectory
+    slabs (rows where either parent has no latent are simply not computed);
+  * decoded frames stay on the device for the LPIPS placement metric (the
+    reference round-trips every frame through PIL and back, :575-579, :750-755);
+    PIL images are produced once per frame for the API;
+  * timing estimates use CUDA events (the reference's time.time() pairs are not
+    synchronised, :110-117).
+"""
+import os
+import time
+import warnings
+from typing import List, Optional
+
+import numpy as np
+import torch
+from PIL import Image
+
+from . import ops
+from .diffusers_holder import DiffusersHolder
+from .next_rows import TorchLPIPSAlex, lpips_random_state_dict
+from .utils import add_frames_linear_interp, interpolate_linear
+
+warnings.filterwarnings('ignore')
+torch.set_grad_enabled(False)
+
+
+class BlendingEngine():
+    def __init__(self, pipe, do_compile: bool = False, guidance_scale_mid_damper: float = 0.5,
+                 mid_compression_scaler: float = 1.2, *, holder=None, similarity_fn=None, run_benchmark=True):
+        assert guidance_scale_mid_damper > 0 and guidance_scale_mid_damper <= 1.0, \
+            f"guidance_scale_mid_damper neees to be in interval (0,1], you provided {guidance_scale_mid_damper}"
+        if do_compile:
+            raise ValueError("do_compile selects the reference's stable-fast/Triton path; this backend is already "
+                             "compiled CUDA (sm_100a) and has no such option")
+        self.dh = holder if holder is not None else DiffusersHolder(pipe)
+        self.device = self.dh.device
+        self.set_dimensions()
+        self.guidance_scale_mid_damper = guidance_scale_mid_damper
+        self.mid_compression_scaler = mid_compression_scaler
+        self.seed1 = 0
+        self.seed2 = 0
+        self.prompt1 = ""
+        self.prompt2 = ""
+        self.tree_latents = [None, None]
+        self.tree_fracts = None
+        self.idx_injection = []
+        self.tree_status = None
+        self.tree_final_imgs = []
+        self.text_embedding1 = None
+        self.text_embedding2 = None
+        self.image1_lowres = None
+        self.image2_lowres = None
+        self.negative_prompt = None
+        self.set_guidance_scale()
+        self.multi_transition_img_first = None
+        self.multi_transition_img_last = None
+        self.dt_unet_step = 0
+        self.dt_vae = 0
+        self._similarity_fn = similarity_fn
+        self.lpips = None
+        if similarity_fn is None:
+            sd = getattr(pipe, "lpips_state_dict", None) or lpips_random_state_dict(2, self.device)
+            self.lpips = TorchLPIPSAlex(sd, self.device)
+        self.set_prompt1("")
+        self.set_prompt2("")
+        self.set_branch1_crossfeed()
+        self.set_parental_crossfeed()
+        self.set_num_inference_steps()
+        if run_benchmark:
+            self.benchmark_speed()
+        else:
+            self.dt_unet_step, self.dt_vae = 0.05, 0.1
+        self.set_branching()
+
+    # ---- timing -------------------------------------------------------------------------------
+    def benchmark_speed(self):
+        """dt_unet_step / dt_vae for the time-based branching planner (blending_engine.py:100-118),
+        measured with a device synchronisation on both sides."""
+        text_embeddings = self.dh.get_text_embedding("test")
+        latents_start = self.dh.get_noise(np.random.randint(111111))
+        N = self.num_inference_steps
+        self.dh.run_diffusion_sd_xl(text_embeddings, latents_start, idx_start=N - 1)      # warm-up
+        torch.cuda.synchronize()
+        t0 = time.time()
+        list_latents = self.dh.run_diffusion_sd_xl(text_embeddings, latents_start, idx_start=N - 1)
+        torch.cuda.synchronize()
+        self.dt_unet_step = time.time() - t0
+        self._decode_frame(list_latents[-1])
+        torch.cuda.synchronize()
+        t0 = time.time()
+        self._decode_frame(list_latents[-1])
+        torch.cuda.synchronize()
+        self.dt_vae = time.time() - t0
+
+    # ---- setters (defaults keyed on the model like the reference) ------------------------------
+    def set_dimensions(self, size_output=None):
+        if size_output is None:
+            size_output = (512, 512) if self.dh.is_sdxl_turbo else (1024, 1024)
+        self.dh.set_dimensions(size_output)
+
+    def set_guidance_scale(self, guidance_scale=None):
+        if guidance_scale is None:
+            guidance_scale = 0.0 if self.dh.is_sdxl_turbo else 4.0
+        self.guidance_scale_base = guidance_scale
+        self.guidance_scale = guidance_scale
+        self.dh.guidance_scale = guidance_scale
+
+    def set_negative_prompt(self, negative_prompt):
+        self.negative_prompt = negative_prompt
+        self.dh.set_negative_prompt(negative_prompt)
+
+    def set_guidance_mid_dampening(self, fract_mixing):
+        mid_factor = 1 - np.abs(fract_mixing - 0.5) / 0.5
+        max_guidance_reduction = self.guidance_scale_base * (1 - self.guidance_scale_mid_damper) - 1
+        guidance_scale_effective = self.guidance_scale_base - max_guidance_reduction * mid_factor
+        self.guidance_scale = guidance_scale_effective
+        self.dh.guidance_scale = guidance_scale_effective
+
+    def set_branch1_crossfeed(self, crossfeed_power=0, crossfeed_range=0, crossfeed_decay=0):
+        self.branch1_crossfeed_power = np.clip(crossfeed_power, 0, 1)
+        self.branch1_crossfeed_range = np.clip(crossfeed_range, 0, 1)
+        self.branch1_crossfeed_decay = np.clip(crossfeed_decay, 0, 1)
+
+    def set_parental_crossfeed(self, crossfeed_power=None, crossfeed_range=None, crossfeed_decay=None):
+        if self.dh.is_sdxl_turbo:
+            crossfeed_power = 1.0 if crossfeed_power is None else crossfeed_power
+            crossfeed_range = 1.0 if crossfeed_range is None else crossfeed_range
+            crossfeed_decay = 1.0 if crossfeed_decay is None else crossfeed_decay
+        else:
+            # the reference overrides whatever the caller passed for the base model (blending_engine.py:200-203)
+            crossfeed_power, crossfeed_range, crossfeed_decay = 0.3, 0.6, 0.9
+        self.parental_crossfeed_power = np.clip(crossfeed_power, 0, 1)
+        self.parental_crossfeed_range = np.clip(crossfeed_range, 0, 1)
+        self.parental_crossfeed_decay = np.clip(crossfeed_decay, 0, 1)
+
+    def set_prompt1(self, prompt: str):
+        prompt = prompt.replace("_", " ")
+        self.prompt1 = prompt
+        self.text_embedding1 = self.get_text_embeddings(self.prompt1)
+
+    def set_prompt2(self, prompt: str):
+        prompt = prompt.replace("_", " ")
+        self.prompt2 = prompt
+        self.text_embedding2 = self.get_text_embeddings(self.prompt2)
+
+    def set_image1(self, image):
+        self.image1_lowres = image
+
+    def set_image2(self, image):
+        self.image2_lowres = image
+
+    def set_num_inference_steps(self, num_inference_steps=None):
+        if num_inference_steps is None:
+            num_inference_steps = 4 if self.dh.is_sdxl_turbo else 30
+        self.num_inference_steps = num_inference_steps
+        self.dh.set_num_inference_steps(num_inference_steps)
+
+    def set_branching(self, depth_strength=None, t_compute_max_allowed=None, nmb_max_branches=None):
+        if self.dh.is_sdxl_turbo:
+            assert t_compute_max_allowed is None, "time-based branching not supported for SDXL Turbo"
+            idx_inject = int(round(self.num_inference_steps * depth_strength)) if depth_strength is not None else 2
+            if nmb_max_branches is None:
+                nmb_max_branches = 10
+            self.list_idx_injection = [idx_inject]
+            self.list_nmb_stems = [nmb_max_branches]
+        else:
+            if depth_strength is None:
+                depth_strength = 0.5
+            if t_compute_max_allowed is None and nmb_max_branches is None:
+                t_compute_max_allowed = 20
+            elif t_compute_max_allowed is not None and nmb_max_branches is not None:
+                raise ValueError("Either specify t_compute_max_allowed or nmb_max_branches")
+            self.list_idx_injection, self.list_nmb_stems = self.get_time_based_branching(
+                depth_strength, t_compute_max_allowed, nmb_max_branches)
+
+    # ---- the transition ---------------------------------------------------------------------------
+    def run_transition(self, recycle_img1: Optional[bool] = False, recycle_img2: Optional[bool] = False,
+                       fixed_seeds: Optional[List[int]] = None):
+        assert self.text_embedding1 is not None, 'Set the first text embedding with .set_prompt1(...) before'
+        assert self.text_embedding2 is not None, 'Set the second text embedding with .set_prompt2(...) before'
+        if fixed_seeds is not None:
+            if isinstance(fixed_seeds, str) and fixed_seeds == 'randomize':
+                fixed_seeds = list(np.random.randint(0, 1000000, 2).astype(np.int32))
+            else:
+                assert len(fixed_seeds) == 2, "Supply a list with len = 2"
+            self.seed1 = fixed_seeds[0]
+            self.seed2 = fixed_seeds[1]
+        N = self.num_inference_steps
+        have1 = self.tree_latents[0] is not None and len(self.tree_latents[0]) == N
+        list_latents1 = self.tree_latents[0] if (recycle_img1 and have1) else self.compute_latents1()
+        have2 = self.tree_latents[-1] is not None and len(self.tree_latents[-1]) == N
+        list_latents2 = self.tree_latents[-1] if (recycle_img2 and have2) else self.compute_latents2()
+
+        self.tree_latents = [list_latents1, list_latents2]
+        self.tree_fracts = [0.0, 1.0]
+        self._tree_frames = [self._decode_frame(list_latents1[-1]), self._decode_frame(list_latents2[-1])]
+        self.tree_idx_injection = [0, 0]
+        # the reference seeds this list with a bound method (blending_engine.py:349); only its length
+        # matters for the first argmax, so a placeholder keeps the same behaviour
+        self.tree_similarities = [None]
+
+        for s_idx in range(len(self.list_idx_injection)):
+            nmb_stems = int(self.list_nmb_stems[s_idx])
+            idx_injection = int(self.list_idx_injection[s_idx])
+            for _ in range(nmb_stems):
+                fract_mixing, b_parent1, b_parent2 = self.get_mixing_parameters(idx_injection)
+                self.set_guidance_mid_dampening(fract_mixing)
+                list_latents = self.compute_latents_mix(fract_mixing, b_parent1, b_parent2, idx_injection)
+                self.insert_into_tree(fract_mixing, idx_injection, list_latents)
+        self.tree_final_imgs = [self._frame_to_pil(f) for f in self._tree_frames]
+        return self.tree_final_imgs
+
+    def compute_latents1(self, return_image=False):
+        list_conditionings = self.get_mixed_conditioning(0)
+        ev0, ev1 = self._events()
+        latents_start = self.get_noise(self.seed1)
+        list_latents1 = self.run_diffusion(list_conditionings, latents_start=latents_start, idx_start=0)
+        self._finish_timing(ev0, ev1)
+        self.tree_latents[0] = list_latents1
+        if return_image:
+            return self.dh.latent2image(list_latents1[-1])
+        return list_latents1
+
+    def compute_latents2(self, return_image=False):
+        list_conditionings = self.get_mixed_conditioning(1)
+        latents_start = self.get_noise(self.seed2)
+        if self.branch1_crossfeed_power > 0.0:
+            N = self.num_inference_steps
+            idx_mixing_stop = int(round(N * self.branch1_crossfeed_range))
+            mixing_coeffs = list(np.linspace(self.branch1_crossfeed_power,
+                                             self.branch1_crossfeed_power * self.branch1_crossfeed_decay,
+                                             idx_mixing_stop))
+            mixing_coeffs.extend((N - idx_mixing_stop) * [0])
+            list_latents2 = self.run_diffusion(list_conditionings, latents_start=latents_start, idx_start=0,
+                                               list_latents_mixing=self.tree_latents[0], mixing_coeffs=mixing_coeffs)
+        else:
+            list_latents2 = self.run_diffusion(list_conditionings, latents_start)
+        self.tree_latents[-1] = list_latents2
+        if return_image:
+            return self.dh.latent2image(list_latents2[-1])
+        return list_latents2
+
+    def _parental_mix(self, traj1, traj2, fract):
+        """One batched slerp over the steps where both parents have latents (blending_engine.py:442-450)."""
+        N = self.num_inference_steps
+        first = 0
+        while first < N and (traj1[first] is None or traj2[first] is None):
+            first += 1
+        out = [None] * N
+        if first == N:
+            return out
+        rows = N - first
+        ref = traj1[first]
+        n = ref.numel()
+
+        def slab(traj):
+            # trajectories produced by the holder are contiguous slabs: rows are `n` elements apart
+            base = traj[first]
+            ok = all(traj[first + r].data_ptr() == base.data_ptr() + r * n * base.element_size() for r in range(rows))
+            if ok:
+                return torch.as_strided(base, (rows, n), (n, 1))
+            return torch.stack([t.reshape(n) for t in traj[first:]], 0)
+
+        if not (torch.is_tensor(ref) and ref.is_cuda):
+            raise RuntimeError("parental mix needs CUDA latents (no CPU fallback)")
+        mixed = ops.slerp_rows(slab(traj1), slab(traj2), float(fract))
+        for r in range(rows):
+            out[first + r] = mixed[r].view(ref.shape)
+        return out
+
+    def compute_latents_mix(self, fract_mixing, b_parent1, b_parent2, idx_injection):
+        list_conditionings = self.get_mixed_conditioning(fract_mixing)
+        fract_mixing_parental = (fract_mixing - self.tree_fracts[b_parent1]) / \
+            (self.tree_fracts[b_parent2] - self.tree_fracts[b_parent1])
+        list_latents_parental_mix = self._parental_mix(self.tree_latents[b_parent1], self.tree_latents[b_parent2],
+                                                       fract_mixing_parental)
+        N = self.num_inference_steps
+        idx_mixing_stop = int(round(N * self.parental_crossfeed_range))
+        mixing_coeffs = idx_injection * [self.parental_crossfeed_power]
+        nmb_mixing = idx_mixing_stop - idx_injection
+        if nmb_mixing > 0:
+            mixing_coeffs.extend(list(np.linspace(self.parental_crossfeed_power,
+                                                  self.parental_crossfeed_power * self.parental_crossfeed_decay,
+                                                  nmb_mixing)))
+        mixing_coeffs.extend((N - len(mixing_coeffs)) * [0])
+        latents_start = list_latents_parental_mix[idx_injection - 1]
+        return self.run_diffusion(list_conditionings, latents_start=latents_start, idx_start=idx_injection,
+                                  list_latents_mixing=list_latents_parental_mix, mixing_coeffs=mixing_coeffs)
+
+    def get_time_based_branching(self, depth_strength, t_compute_max_allowed=None, nmb_max_branches=None):
+        N = self.num_inference_steps
+        idx_injection_base = int(np.floor(N * depth_strength))
+        steps = int(np.ceil(N / 10))
+        list_idx_injection = np.arange(idx_injection_base, N, steps)
+        list_nmb_stems = np.ones(len(list_idx_injection), dtype=np.int32)
+        if nmb_max_branches is None:
+            assert t_compute_max_allowed is not None, "Either specify t_compute_max_allowed or nmb_max_branches"
+            stop_criterion = "t_compute_max_allowed"
+        elif t_compute_max_allowed is None:
+            stop_criterion = "nmb_max_branches"
+            nmb_max_branches -= 2  # the two outer frames
+        else:
+            raise ValueError("Either specify t_compute_max_allowed or nmb_max_branches")
+        stop, first_iteration = False, True
+        while not stop:
+            list_compute_steps = (N - list_idx_injection) * list_nmb_stems
+            t_compute = np.sum(list_compute_steps) * self.dt_unet_step + self.dt_vae * np.sum(list_nmb_stems)
+            t_compute += 2 * (N * self.dt_unet_step + self.dt_vae)
+            increased = False
+            for s_idx in range(len(list_nmb_stems) - 1):
+                if list_nmb_stems[s_idx + 1] / list_nmb_stems[s_idx] >= 1:
+                    list_nmb_stems[s_idx] += 1
+                    increased = True
+                    break
+            if not increased:
+                list_nmb_stems[-1] += 1
+            if stop_criterion == "t_compute_max_allowed" and t_compute > t_compute_max_allowed:
+                stop = True
+            elif stop_criterion == "nmb_max_branches" and np.sum(list_nmb_stems) >= nmb_max_branches:
+                stop = True
+                if first_iteration:
+                    list_idx_injection = np.linspace(list_idx_injection[0], list_idx_injection[-1],
+                                                     nmb_max_branches).astype(np.int32)
+                    list_nmb_stems = np.ones(len(list_idx_injection), dtype=np.int32)
+            else:
+                first_iteration = False
+        return list_idx_injection, list_nmb_stems
+
+    def get_mixing_parameters(self, idx_injection):
+        similarities = self.tree_similarities
+        b_closest1 = 0 if len(similarities) == 1 else int(np.argmax(similarities))
+        b_closest2 = b_closest1 + 1
+        fract_mixing = (self.tree_fracts[b_closest1] + self.tree_fracts[b_closest2]) / 2
+        b_parent1 = b_closest1
+        while self.tree_idx_injection[b_parent1] >= idx_injection:
+            b_parent1 -= 1
+        b_parent2 = b_closest2
+        while self.tree_idx_injection[b_parent2] >= idx_injection:
+            b_parent2 += 1
+        return fract_mixing, b_parent1, b_parent2
+
+    def insert_into_tree(self, fract_mixing, idx_injection, list_latents):
+        frame = self._decode_frame(list_latents[-1])
+        b_parent1, b_parent2 = self.get_closest_idx(fract_mixing)
+        left_sim = self.get_lpips_similarity(frame, self._tree_frames[b_parent1])
+        right_sim = self.get_lpips_similarity(frame, self._tree_frames[b_parent2])
+        idx_insert = b_parent1 + 1
+        self.tree_latents.insert(idx_insert, list_latents)
+        self._tree_frames.insert(idx_insert, frame)
+        self.tree_fracts.insert(idx_insert, fract_mixing)
+        self.tree_idx_injection.insert(idx_insert, idx_injection)
+        self.tree_similarities[b_parent1] = left_sim
+        self.tree_similarities.insert(idx_insert, right_sim)
+
+    def get_noise(self, seed):
+        return self.dh.get_noise(seed)
+
+    @torch.no_grad()
+    def run_diffusion(self, list_conditionings, latents_start=None, idx_start=0, list_latents_mixing=None,
+                      mixing_coeffs=0.0, return_image=False):
+        self.dh.set_num_inference_steps(self.num_inference_steps)
+        assert type(list_conditionings) is list, "list_conditionings need to be a list"
+        return self.dh.run_diffusion_sd_xl(text_embeddings=list_conditionings[0], latents_start=latents_start,
+                                           idx_start=idx_start, list_latents_mixing=list_latents_mixing,
+                                           mixing_coeffs=mixing_coeffs, return_image=return_image)
+
+    @torch.no_grad()
+    def get_mixed_conditioning(self, fract_mixing):
+        mix = [None if a is None else interpolate_linear(a, b, fract_mixing)
+               for a, b in zip(self.text_embedding1, self.text_embedding2)]
+        return [mix]
+
+    @torch.no_grad()
+    def get_text_embeddings(self, prompt: str):
+        return self.dh.get_text_embedding(prompt)
+
+    # ---- outputs ------------------------------------------------------------------------------------
+    def write_imgs_transition(self, dp_img):
+        os.makedirs(dp_img, exist_ok=True)
+        for i, img in enumerate(self.tree_final_imgs):
+            img.save(os.path.join(dp_img, f"lowres_img_{str(i).zfill(4)}.jpg"))
+
+    def write_movie_transition(self, fp_movie, duration_transition, fps=30):
+        """Fill up to duration*fps frames by linear interpolation and encode with OpenCV
+        (the reference uses lunar_tools.MovieSaver/ffmpeg, blending_engine.py:684-706)."""
+        import cv2
+        frames = add_frames_linear_interp([np.asarray(im) for im in self.tree_final_imgs], fps_target=fps,
+                                          duration_target=duration_transition)
+        if os.path.isfile(fp_movie):
+            os.remove(fp_movie)
+        h, w = self.dh.height_img, self.dh.width_img
+        vw = cv2.VideoWriter(fp_movie, cv2.VideoWriter_fourcc(*"mp4v"), fps, (w, h))
+        for f in frames:
+            f = np.asarray(f)
+            if f.shape[0] != h or f.shape[1] != w:
+                f = cv2.resize(f, (w, h))
+            vw.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+        vw.release()
+
+    def get_state_dict(self):
+        state_dict = {}
+        for v in ['prompt1', 'prompt2', 'seed1', 'seed2', 'num_inference_steps', 'guidance_scale',
+                  'guidance_scale_mid_damper', 'mid_compression_scaler', 'negative_prompt',
+                  'branch1_crossfeed_power', 'branch1_crossfeed_range', 'branch1_crossfeed_decay',
+                  'parental_crossfeed_power', 'parental_crossfeed_range', 'parental_crossfeed_decay']:
+            if hasattr(self, v):
+                val = getattr(self, v)
+                if v in ('seed1', 'seed2'):
+                    val = int(val)
+                elif v == 'guidance_scale' or isinstance(val, (np.floating,)):
+                    val = float(val)
+                state_dict[v] = val
+        return state_dict
+
+    def swap_forward(self):
+        self.tree_latents[0] = self.tree_latents[-1]
+        self.prompt1 = self.prompt2
+        self.text_embedding1 = self.text_embedding2
+        self.tree_final_imgs = []
+
+    # ---- similarity / helpers ---------------------------------------------------------------------------
+    def get_lpips_similarity(self, imgA, imgB):
+        """High values = dissimilar.  Accepts device uint8 frames (internal) or PIL/numpy images (API parity)."""
+        if self._similarity_fn is not None:
+            return self._similarity_fn(self._to_numpy(imgA), self._to_numpy(imgB))
+        return self.lpips.distance(self._to_device_frame(imgA), self._to_device_frame(imgB))
+
+    def get_tree_similarities(self):
+        return [self.get_lpips_similarity(self._tree_frames[i], self._tree_frames[i + 1])
+                for i in range(len(self._tree_frames) - 1)]
+
+    def get_closest_idx(self, fract_mixing: float):
+        pdist = fract_mixing - np.asarray(self.tree_fracts)
+        pdist_pos = pdist.copy()
+        pdist_pos[pdist_pos < 0] = np.inf
+        b_parent1 = int(np.argmin(pdist_pos))
+        pdist_neg = -pdist.copy()
+        pdist_neg[pdist_neg <= 0] = np.inf
+        b_parent2 = int(np.argmin(pdist_neg))
+        if b_parent1 > b_parent2:
+            b_parent1, b_parent2 = b_parent2, b_parent1
+        return b_parent1, b_parent2
+
+    def _decode_frame(self, latents):
+        if hasattr(self.dh, "decode_to_device"):
+            return self.dh.decode_to_device(latents)
+        return self.dh.latent2image(latents)          # foreign holder (tests): whatever it returns
+
+    def _frame_to_pil(self, frame):
+        if torch.is_tensor(frame):
+            return Image.fromarray(frame.cpu().numpy())
+        return frame
+
+    def _to_numpy(self, img):
+        return img.cpu().numpy() if torch.is_tensor(img) else np.asarray(img)
+
+    def _to_device_frame(self, img):
+        if torch.is_tensor(img):
+            return img
+        return torch.from_numpy(np.asarray(img)).to(self.device)
+
+    def _events(self):
+        if torch.cuda.is_available():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            return e0, e1
+        return time.time(), None
+
+    def _finish_timing(self, e0, e1):
+        if e1 is None:
+            self.dt_unet_step = (time.time() - e0) / self.num_inference_steps
+            return
+        e1.record()
+        self._pending_timing = (e0, e1)       # resolved lazily: no host sync inside the transition

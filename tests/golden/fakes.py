@@ -11,9 +11,9 @@ import torch
 
 
 class FakeHolder:
-    def __init__(self, turbo=False, h=8, w=8):
+    def __init__(self, turbo=False, h=8, w=8, device="cpu"):
         self.is_sdxl_turbo = turbo
-        self.device = "cpu"
+        self.device = device
         self.pipe = None
         self.guidance_scale = 5.0
         self.num_inference_steps = 30
@@ -33,21 +33,21 @@ class FakeHolder:
 
     def get_text_embedding(self, prompt):
         g = torch.Generator().manual_seed(sum(ord(c) for c in prompt) + 7)
-        pe = torch.randn(1, 5, 16, generator=g)
-        pp = torch.randn(1, 8, generator=g)
+        pe = torch.randn(1, 5, 16, generator=g).to(self.device)
+        pp = torch.randn(1, 8, generator=g).to(self.device)
         if self.guidance_scale > 1:
             return pe, pe * 0.1, pp, pp * 0.1
         return pe, None, pp, None
 
     def get_noise(self, seed=420):
         g = torch.Generator().manual_seed(int(seed))
-        return torch.randn(1, 4, self.height_latent, self.width_latent, generator=g).half()
+        return torch.randn(1, 4, self.height_latent, self.width_latent, generator=g).half().to(self.device)
 
     def latent2image(self, latents, output_type="pil"):
         x = latents.float()[0, :3]
         x = torch.nn.functional.interpolate(x[None], scale_factor=8, mode="nearest")[0]
         img = ((torch.tanh(x) * 0.5 + 0.5) * 255).round().clamp(0, 255).byte()
-        return img.permute(1, 2, 0).numpy()
+        return img.permute(1, 2, 0).cpu().numpy()
 
     def run_diffusion_sd_xl(self, text_embeddings, latents_start, idx_start=0,
                             list_latents_mixing=None, mixing_coeffs=0.0, return_image=False):

@@ -1,0 +1,192 @@
+"""GPU tests of the product BlendingEngine / DiffusersHolder.
+
+1. Tree logic vs the REFERENCE's own BlendingEngine (tests/golden/tree.json), with the
+   FakeHolder producing CUDA latents so the parental mix runs through lb_slerp_rows.
+2. Denoise loop (run_diffusion_sd_xl) vs the oracle holder on a tiny SDXL-shaped UNet:
+   restart-reproducibility, crossfeed, CFG / no-CFG, Euler and Euler-ancestral.
+3. Whole transition (tiny UNet + VAE + LPIPS) vs the oracle engine: identical tree.
+Tolerances are stated at each assert."""
+import dataclasses
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _cases():
+    with open(os.path.join(GOLD, "tree.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c["name"])
+def test_tree_logic_matches_reference_engine(case):
+    from fakes import FakeHolder, fake_similarity
+    from latentblending_b200 import BlendingEngine
+    dh = FakeHolder(turbo=case["turbo"], device="cuda")
+    be = BlendingEngine(None, holder=dh, similarity_fn=fake_similarity, run_benchmark=False)
+    be.set_num_inference_steps(None if case["n_steps"] in (4, 30) else case["n_steps"])
+    if case["branch1"]:
+        be.set_branch1_crossfeed(*case["branch1"])
+    be.set_branching(**case["branching"])
+    assert [int(v) for v in be.list_idx_injection] == case["list_idx_injection"]
+    assert [int(v) for v in be.list_nmb_stems] == case["list_nmb_stems"]
+    for t, gold in enumerate(case["transitions"]):
+        if t == 0:
+            be.set_prompt1(case["prompts"][0])
+            be.set_prompt2(case["prompts"][1])
+            recycle = False
+        else:
+            be.swap_forward()
+            be.set_prompt2(case["prompts"][t + 1])
+            recycle = True
+        dh.calls.clear()
+        imgs = be.run_transition(recycle_img1=recycle, fixed_seeds=case["seeds"][t:t + 2])
+        assert be.tree_fracts == gold["tree_fracts"]
+        assert [int(v) for v in be.tree_idx_injection] == gold["tree_idx_injection"]
+        assert len(imgs) == gold["n_imgs"] == len(be.tree_latents)
+        # similarities are means of |uint8 diffs|: CUDA vs CPU sin() may flip a pixel by 1 -> 1e-4 slack
+        np.testing.assert_allclose(be.tree_similarities, gold["tree_similarities"], rtol=0, atol=1e-4)
+        assert len(dh.calls) == len(gold["calls"])
+        for a, b in zip(dh.calls, gold["calls"]):
+            assert a["idx_start"] == b["idx_start"] and a["guidance"] == b["guidance"]
+            assert a["n_mix_none"] == b["n_mix_none"]
+            if isinstance(b["coeffs"], list):
+                np.testing.assert_allclose(a["coeffs"], b["coeffs"], rtol=0, atol=0)
+            else:
+                assert a["coeffs"] == b["coeffs"]
+            assert abs(a["start_sum"] - b["start_sum"]) <= 2e-2 * max(1.0, abs(b["start_sum"]))
+
+
+# ---- tiny real pipeline -------------------------------------------------------------------------
+def _pair(turbo, seed=0):
+    from latentblending_b200 import SyntheticSDXLPipe
+    from latentblending_b200.unet import UNetConfig
+    from oracle.lpips_alex import LPIPSAlex
+    from oracle.pipe import OraclePipe
+    from oracle.sdxl_unet import tiny_config
+    from oracle.vae import tiny_vae_config
+    name = "synthetic/sdxl-turbo-tiny" if turbo else "synthetic/sdxl-base-tiny"
+    ocfg = tiny_config()
+    op = OraclePipe(name, unet_cfg=ocfg, vae_cfg=tiny_vae_config(), seed=seed)
+    with torch.no_grad():
+        for m in (op.unet, op.vae):
+            for p in m.parameters():
+                p.copy_(p.half().float())
+    lp = LPIPSAlex(seed=2)
+    cfg = UNetConfig(**{f.name: getattr(ocfg, f.name) for f in dataclasses.fields(ocfg)})
+    pp = SyntheticSDXLPipe(name, "cuda:0", unet_cfg=cfg, unet_state_dict=op.unet.state_dict(),
+                           vae_state_dict=op.vae.state_dict(), vae_channels=tiny_vae_config().block_out_channels,
+                           lpips_state_dict={k: v for k, v in lp.state_dict().items() if "s." in k})
+    return op, pp, lp
+
+
+def _rel(a, b):
+    return ((a.float().cpu() - b.float()).norm() / b.float().norm()).item()
+
+
+@pytest.mark.parametrize("turbo", [False, True])
+def test_denoise_loop_matches_oracle_holder(turbo):
+    from latentblending_b200 import DiffusersHolder
+    from oracle.holder import OracleHolder
+    op, pp, _ = _pair(turbo)
+    oh, dh = OracleHolder(op), DiffusersHolder(pp)
+    N = 4 if turbo else 6
+    for h in (oh, dh):
+        h.guidance_scale = 0.0 if turbo else 4.0
+        h.set_dimensions((128, 128))
+        h.set_num_inference_steps(N)
+    g = torch.Generator().manual_seed(5)
+    noises = [torch.randn(1, 4, 16, 16, generator=g).half() for _ in range(N)]
+    oh.noise_fn = lambda i, shape: noises[i]
+    dh.noise_fn = lambda i, shape: noises[i]
+    emb_o, emb_d = oh.get_text_embedding("a lake"), dh.get_text_embedding("a lake")
+    for a, b in zip(emb_o, emb_d):
+        assert (a is None and b is None) or torch.equal(a, b.cpu())
+    start = oh.get_noise(420)
+    ref = oh.run_diffusion_sd_xl(emb_o, start)
+    got = dh.run_diffusion_sd_xl(emb_d, start.cuda())
+    assert len(got) == N
+    for i in range(N):
+        assert _rel(got[i], ref[i]) <= 2e-2, f"step {i}: {_rel(got[i], ref[i])}"     # fp16 UNet drift over steps
+    # restart reproducibility (diffusers_holder.py:456-457): restarting from step k-1's latent reproduces the tail
+    k = 2
+    tail = dh.run_diffusion_sd_xl(emb_d, got[k - 1], idx_start=k)
+    assert tail[:k] == [None] * k
+    for i in range(k, N):
+        assert torch.equal(tail[i], got[i])
+    # crossfeed toward another trajectory, coefficients as a list
+    other = [t.cuda() for t in oh.run_diffusion_sd_xl(emb_o, oh.get_noise(421))]
+    coeffs = [0.0, 0.5, 0.25] + [0.0] * (N - 3)
+    ref_x = oh.run_diffusion_sd_xl(emb_o, start, 0, [t.cpu() for t in other], coeffs)
+    got_x = dh.run_diffusion_sd_xl(emb_d, start.cuda(), 0, other, coeffs)
+    assert _rel(got_x[-1], ref_x[-1]) <= 2e-2
+    assert not torch.equal(got_x[-1], got[-1])
+    with pytest.raises(AssertionError):
+        dh.run_diffusion_sd_xl(emb_d, start.cuda(), 0, other, coeffs[:-1])
+    with pytest.raises(ValueError):
+        dh.run_diffusion_sd_xl(emb_d, start.cuda(), 0, other, 1)
+
+
+@pytest.mark.parametrize("turbo", [False, True])
+def test_whole_transition_matches_oracle_engine(turbo):
+    from latentblending_b200 import BlendingEngine
+    from oracle.engine import OracleEngine
+    from oracle.holder import OracleHolder
+    op, pp, lp = _pair(turbo, seed=3)
+    oe = OracleEngine(OracleHolder(op), lpips_net=lp)
+    be = BlendingEngine(pp, run_benchmark=False)
+    N = 4 if turbo else 8
+    g = torch.Generator().manual_seed(11)
+    noise_bank = {}
+
+    def noise_for(key, shape):
+        if key not in noise_bank:
+            noise_bank[key] = torch.randn(shape, generator=g).half()
+        return noise_bank[key]
+    # identical start noise on both sides (CPU vs CUDA generators differ), identical ancestral noise per call/step
+    be.dh.get_noise = lambda seed: oe.dh.get_noise(seed).cuda()
+    calls = {"o": 0, "b": 0}
+    o_run, b_run = oe.dh.run_diffusion_sd_xl, be.dh.run_diffusion_sd_xl
+
+    def wrap(run, holder, tag):
+        def f(*a, **k):
+            c = calls[tag]
+            calls[tag] += 1
+            holder.noise_fn = lambda i, shape: noise_for((c, i), shape)
+            return run(*a, **k)
+        return f
+    oe.dh.run_diffusion_sd_xl = wrap(o_run, oe.dh, "o")
+    be.dh.run_diffusion_sd_xl = wrap(b_run, be.dh, "b")
+    for e in (oe, be):
+        e.set_dimensions((128, 128))
+        e.set_num_inference_steps(N)
+        e.set_prompt1("photo of a lake")
+        e.set_prompt2("alien planet")
+        if turbo:
+            e.set_branching(nmb_max_branches=3)
+        else:
+            e.set_branch1_crossfeed(0.6, 0.5, 0.8)
+            e.set_branching(depth_strength=0.5, nmb_max_branches=6)
+    assert [int(v) for v in be.list_idx_injection] == [int(v) for v in oe.list_idx_injection]
+    imgs_o = oe.run_transition(fixed_seeds=[420, 421])
+    imgs_b = be.run_transition(fixed_seeds=[420, 421])
+    assert be.tree_fracts == oe.tree_fracts
+    assert [int(v) for v in be.tree_idx_injection] == [int(v) for v in oe.tree_idx_injection]
+    assert len(imgs_b) == len(imgs_o) == len(be.tree_latents)
+    for tb, to in zip(be.tree_latents, oe.tree_latents):
+        assert [x is None for x in tb] == [x is None for x in to]
+        assert _rel(tb[-1], to[-1]) <= 5e-2
+    for ib, io in zip(imgs_b, imgs_o):
+        d = np.abs(np.asarray(ib).astype(np.int32) - np.asarray(io).astype(np.int32))
+        assert d.mean() <= 3.0, d.mean()           # uint8 levels
+    # write_movie_transition produces a file with the requested frame count
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        fp = os.path.join(td, "t.mp4")
+        be.write_movie_transition(fp, duration_transition=1, fps=10)
+        assert os.path.getsize(fp) > 0
