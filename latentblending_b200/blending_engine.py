@@ -265,7 +265,10 @@ class BlendingEngine():
         def slab(traj):
             # trajectories produced by the holder are contiguous slabs: rows are `n` elements apart
             base = traj[first]
-            ok = all(traj[first + r].data_ptr() == base.data_ptr() + r * n * base.element_size() for r in range(rows))
+            store = base.untyped_storage().data_ptr()
+            ok = all(traj[first + r].untyped_storage().data_ptr() == store and
+                     traj[first + r].data_ptr() == base.data_ptr() + r * n * base.element_size()
+                     for r in range(rows))
             if ok:
                 return torch.as_strided(base, (rows, n), (n, 1))
             return torch.stack([t.reshape(n) for t in traj[first:]], 0)

@@ -41,7 +41,7 @@ class DiffusersHolder:
         self.width_latent = self.height_latent = s
         self.width_img = self.height_img = s * pipe.vae_scale_factor
         self.unet = UNetB200(pipe.unet_cfg, pipe.unet_state_dict, self.device)
-        self.vae = TorchVAEDecoder(pipe.vae_state_dict, n_up_blocks=len(pipe.vae_channels),
+        self.vae = TorchVAEDecoder(pipe.vae_state_dict, self.device, n_up_blocks=len(pipe.vae_channels),
                                    scaling_factor=pipe.vae_scaling_factor)
         self.noise_fn = None          # tests: inject the ancestral-step noise, noise_fn(i, shape)
         self._cond_key = None

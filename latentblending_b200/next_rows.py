@@ -33,8 +33,8 @@ def _resnet(x, sd, n):
 class TorchVAEDecoder:
     """AutoencoderKL decoder (SDXL VAE topology) as functional PyTorch over a diffusers-named state dict."""
 
-    def __init__(self, state_dict, n_up_blocks=4, scaling_factor=0.13025, dtype=torch.float16):
-        self.sd = {k: v.to(dtype) for k, v in state_dict.items()}
+    def __init__(self, state_dict, device, n_up_blocks=4, scaling_factor=0.13025, dtype=torch.float16):
+        self.sd = {k: v.detach().to(device=device, dtype=dtype) for k, v in state_dict.items()}
         self.n_up = n_up_blocks
         self.scaling_factor = scaling_factor
         self.dtype = dtype

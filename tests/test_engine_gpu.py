@@ -173,8 +173,25 @@ def test_whole_transition_matches_oracle_engine(turbo):
             e.set_branch1_crossfeed(0.6, 0.5, 0.8)
             e.set_branching(depth_strength=0.5, nmb_max_branches=6)
     assert [int(v) for v in be.list_idx_injection] == [int(v) for v in oe.list_idx_injection]
+    # The greedy placement takes an argmax over LPIPS gaps; with random weights the gaps can be near-ties that
+    # an fp16-vs-fp32 difference flips.  So: the product computes its own LPIPS on its own frames, each value is
+    # checked against the oracle's value for the same comparison (stated tolerance 5 % + 1e-3), and the decision
+    # then uses the oracle's value so both trees stay comparable branch by branch.
+    o_sims = []
+    o_sim = oe.similarity
+    oe.similarity = lambda a, b: (o_sims.append(o_sim(a, b)) or o_sims[-1])
     imgs_o = oe.run_transition(fixed_seeds=[420, 421])
+    b_real = be.get_lpips_similarity
+    b_count = [0]
+
+    def checked(a, b):
+        v, r = b_real(a, b), o_sims[b_count[0]]
+        b_count[0] += 1
+        assert abs(v - r) <= 0.05 * abs(r) + 1e-3, f"LPIPS call {b_count[0]}: product {v} vs oracle {r}"
+        return r
+    be.get_lpips_similarity = checked
     imgs_b = be.run_transition(fixed_seeds=[420, 421])
+    assert b_count[0] == len(o_sims)
     assert be.tree_fracts == oe.tree_fracts
     assert [int(v) for v in be.tree_idx_injection] == [int(v) for v in oe.tree_idx_injection]
     assert len(imgs_b) == len(imgs_o) == len(be.tree_latents)
