@@ -66,6 +66,8 @@ class BlendingEngine():
         self.dt_unet_step = 0
         self.dt_vae = 0
         self._similarity_fn = similarity_fn
+        self.output_device_frames = False     # True: run_transition returns uint8 device frames, no D2H / PIL
+        self.d2h_bytes = 0                    # bytes copied device->host for returned frames (bench e2e)
         self.lpips = None
         if similarity_fn is None:
             sd = getattr(pipe, "lpips_state_dict", None) or lpips_random_state_dict(2, self.device)
@@ -216,7 +218,10 @@ class BlendingEngine():
                 self.set_guidance_mid_dampening(fract_mixing)
                 list_latents = self.compute_latents_mix(fract_mixing, b_parent1, b_parent2, idx_injection)
                 self.insert_into_tree(fract_mixing, idx_injection, list_latents)
-        self.tree_final_imgs = [self._frame_to_pil(f) for f in self._tree_frames]
+        if self.output_device_frames:
+            self.tree_final_imgs = list(self._tree_frames)
+        else:
+            self.tree_final_imgs = [self._frame_to_pil(f) for f in self._tree_frames]
         return self.tree_final_imgs
 
     def compute_latents1(self, return_image=False):
@@ -460,6 +465,7 @@ class BlendingEngine():
 
     def _frame_to_pil(self, frame):
         if torch.is_tensor(frame):
+            self.d2h_bytes += frame.numel() * frame.element_size()
             return Image.fromarray(frame.cpu().numpy())
         return frame
 

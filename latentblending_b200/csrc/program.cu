@@ -77,12 +77,25 @@ extern "C" int64_t lb_program_num_launches(lb_program* prog) {
 }
 
 extern "C" int lb_program_run(lb_program* prog, float t, void* stream) {
+    return lb_program_run_kinds(prog, t, 0xFFFFFFFFu, stream);
+}
+
+extern "C" int64_t lb_program_count_kinds(lb_program* prog, uint32_t kind_mask) {
+    if (!prog) return -1;
+    int64_t n = 0;
+    for (auto& nd : prog->nodes)
+        if (kind_mask & (1u << nd.op.kind)) n += (nd.op.kind == LB_OP_GROUPNORM) ? 2 : 1;
+    return n;
+}
+
+extern "C" int lb_program_run_kinds(lb_program* prog, float t, uint32_t kind_mask, void* stream) {
     LB_REQUIRE(prog != nullptr, "lb_program_run: null program");
     lb_ctx* ctx = prog->ctx;
     cudaStream_t st = lb_stream(stream);
     for (size_t i = 0; i < prog->nodes.size(); ++i) {
         lb_program::Node& nd = prog->nodes[i];
         const lb_op& o = nd.op;
+        if (!(kind_mask & (1u << o.kind))) continue;
         int e = 0;
         switch (o.kind) {
             case LB_OP_GEMM: e = gemm_plan_launch(nd.gemm, st); break;

@@ -8,6 +8,7 @@ from . import _cabi
 from ._cabi import check, ctx, ptr, stream_ptr
 
 _DT = {torch.float16: 0, torch.float32: 1}
+LAUNCHES = [0]      # kernels of liblb200 launched through this module / Program.run (bench.py reports it)
 
 
 def _dev(t):
@@ -43,6 +44,7 @@ def slerp_rows(p0, p1, fract, out=None, fract_rows=None):
                             p0.stride(0) if rows > 1 else n, p1.stride(0) if rows > 1 else n,
                             out.stride(0) if rows > 1 else n, _DT[p0.dtype], float(fract),
                             ptr(fract_rows), ptr(ws), stream_ptr()), "lb_slerp_rows")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -52,6 +54,7 @@ def lerp(p0, p1, fract):
     out = torch.empty_like(p0)
     check(_cabi.load().lb_lerp(ctx(dev), ptr(p0), ptr(p1), ptr(out), p0.numel(), _DT[p0.dtype], float(fract),
                                stream_ptr()), "lb_lerp")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -63,6 +66,7 @@ def scale_model_input(latents, batch, divisor, out=None):
         out = torch.empty((batch,) + tuple(latents.shape[1:]), dtype=torch.float16, device=latents.device)
     check(_cabi.load().lb_scale_model_input(ctx(dev), ptr(latents), ptr(out), n, int(batch), float(divisor),
                                             stream_ptr()), "lb_scale_model_input")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -79,6 +83,7 @@ def cfg_euler_step(latents, eps, guidance, sigma, dt, sigma_up=0.0, noise=None, 
     check(_cabi.load().lb_cfg_euler_step(ctx(dev), ptr(latents), ptr(eps), ptr(noise), ptr(out), ptr(traj), n,
                                          int(use_cfg), float(np.float32(guidance)), float(sigma), float(dt),
                                          float(sigma_up), stream_ptr()), "lb_cfg_euler_step")
+    LAUNCHES[0] += 1
     return out
 
 

@@ -196,6 +196,7 @@ class SyntheticSDXLPipe:
             random_state_dict(vae_param_shapes(vae_channels), seed + 1, self.device, damp=0.3)
         self.vae_scaling_factor = 0.13025
         self.lpips_state_dict = lpips_state_dict
+        self.h2d_bytes = 0        # bytes of conditioning copied host->device (bench e2e)
 
     def encode_prompt(self, prompt, negative_prompt=None, do_classifier_free_guidance=True, dtype=torch.float16):
         """Synthetic stand-in for StableDiffusionXLPipeline.encode_prompt (diffusers_holder.py:81-95)."""
@@ -205,7 +206,9 @@ class SyntheticSDXLPipe:
             g = torch.Generator().manual_seed(prompt_seed(text))
             e = (torch.randn(1, 77, c.cross_attention_dim, generator=g) * 0.5).to(dtype)
             p = torch.randn(1, c.pooled_dim, generator=g).to(dtype)
-            return e.to(self.device), p.to(self.device)
+            e, p = e.pin_memory(), p.pin_memory()
+            self.h2d_bytes += e.numel() * e.element_size() + p.numel() * p.element_size()
+            return e.to(self.device, non_blocking=True), p.to(self.device, non_blocking=True)
 
         pe, pp = emb(prompt)
         if not do_classifier_free_guidance:

@@ -164,6 +164,32 @@ class Program:
 
     def run(self, t=0.0):
         check(_cabi.load().lb_program_run(self.handle, float(t), stream_ptr()), "lb_program_run")
+        from . import ops
+        ops.LAUNCHES[0] += self.num_launches
+
+    def run_kinds(self, kinds, t=0.0):
+        """Profiling aid: replay only ops of the given kinds (e.g. [OP_GEMM])."""
+        mask = 0
+        for k in kinds:
+            mask |= 1 << k
+        check(_cabi.load().lb_program_run_kinds(self.handle, float(t), mask, stream_ptr()), "lb_program_run_kinds")
+        return int(_cabi.load().lb_program_count_kinds(self.handle, mask))
+
+    def work(self):
+        """Algorithmic work of the recorded ops: {'gemm_flops', 'attn_flops', 'norm_bytes'}."""
+        gemm = attn = norm = 0
+        for op in self.ops:
+            if op.kind == OP_GEMM:
+                d = op.u.gemm
+                gemm += 2 * d.B * d.H * d.W * d.N * (d.taps * d.a0_c + (d.a1_c if d.a1 else 0))
+            elif op.kind == OP_ATTENTION:
+                d = op.u.attn
+                attn += 4 * d.B * d.heads * d.Sq * d.Skv * d.head_dim
+            elif op.kind in (OP_GROUPNORM, OP_LAYERNORM):
+                d = op.u.norm
+                rows = d.rows * (d.B if op.kind == OP_GROUPNORM else 1)
+                norm += 4 * rows * d.C
+        return dict(gemm_flops=gemm, attn_flops=attn, norm_bytes=norm)
 
     def __del__(self):
         try:
