@@ -198,8 +198,11 @@ class BlendingEngine():
             self.seed2 = fixed_seeds[1]
         N = self.num_inference_steps
         have1 = self.tree_latents[0] is not None and len(self.tree_latents[0]) == N
-        list_latents1 = self.tree_latents[0] if (recycle_img1 and have1) else self.compute_latents1()
         have2 = self.tree_latents[-1] is not None and len(self.tree_latents[-1]) == N
+        rank, world = self._dist()
+        if world > 1:
+            return self._run_transition_sharded(recycle_img1 and have1, recycle_img2 and have2, rank, world)
+        list_latents1 = self.tree_latents[0] if (recycle_img1 and have1) else self.compute_latents1()
         list_latents2 = self.tree_latents[-1] if (recycle_img2 and have2) else self.compute_latents2()
 
         self.tree_latents = [list_latents1, list_latents2]
@@ -218,6 +221,79 @@ class BlendingEngine():
                 self.set_guidance_mid_dampening(fract_mixing)
                 list_latents = self.compute_latents_mix(fract_mixing, b_parent1, b_parent2, idx_injection)
                 self.insert_into_tree(fract_mixing, idx_injection, list_latents)
+        if self.output_device_frames:
+            self.tree_final_imgs = list(self._tree_frames)
+        else:
+            self.tree_final_imgs = [self._frame_to_pil(f) for f in self._tree_frames]
+        return self.tree_final_imgs
+
+    # ---- multi-GPU: branches of a level sharded over the ranks (latentblending_b200/sharding.py) -----------
+    @staticmethod
+    def _dist():
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    @property
+    def frames(self):
+        return self._tree_frames
+
+    def _bcast_trajectory(self, traj, src):
+        """Make a full trajectory (list of N latents) computed on rank ``src`` available on every rank."""
+        import torch.distributed as dist
+        N = self.num_inference_steps
+        lat_shape = (1, 4, self.dh.height_latent, self.dh.width_latent)
+        n = int(np.prod(lat_shape))
+        if traj is not None:
+            slab = torch.stack([t.reshape(n) for t in traj], 0).contiguous()
+        else:
+            slab = torch.empty((N, n), dtype=torch.float16, device=self.device)
+        dist.broadcast(slab, src=src)
+        return [slab[i].view(lat_shape) for i in range(N)]
+
+    def _run_transition_sharded(self, reuse1, reuse2, rank, world):
+        import torch.distributed as dist
+        from .sharding import LevelSharder
+        N = self.num_inference_steps
+        seeds = [int(self.seed1), int(self.seed2)]
+        dist.broadcast_object_list(seeds, src=0)            # 'randomize' draws must agree across ranks
+        self.seed1, self.seed2 = seeds
+        crossfed = self.branch1_crossfeed_power > 0.0
+        t1 = self.tree_latents[0] if reuse1 else None
+        t2 = self.tree_latents[-1] if reuse2 else None
+        if not reuse1:
+            mine = self.compute_latents1() if rank == 0 else None
+            if crossfed or reuse2:
+                t1 = self._bcast_trajectory(mine, 0)        # branch 2 reads branch 1 step by step
+                self.tree_latents[0] = t1
+        if not reuse2:
+            owner = 0 if crossfed else 1
+            mine2 = self.compute_latents2() if rank == owner else None
+            if t1 is None:
+                t1 = self._bcast_trajectory(mine, 0)
+            t2 = self._bcast_trajectory(mine2, owner)
+        elif t1 is None:
+            t1 = self._bcast_trajectory(mine, 0)
+        self.tree_latents = [t1, t2]
+        self.tree_fracts = [0.0, 1.0]
+        self._tree_frames = [self._decode_frame(t1[-1]), self._decode_frame(t2[-1])]
+        self.tree_idx_injection = [0, 0]
+        self.tree_similarities = [None]
+        sharder = LevelSharder(rank, world, device=self.device)
+
+        def compute(fract, p1, p2, idx_injection):
+            self.set_guidance_mid_dampening(fract)
+            traj = self.compute_latents_mix(fract, p1, p2, idx_injection)
+            return traj, self._decode_frame(traj[-1])
+
+        def similarity(fa, fb):
+            return self.get_lpips_similarity(fa, fb) if rank == 0 else 0.0
+
+        for s_idx in range(len(self.list_idx_injection)):
+            sharder.run_level(self, int(self.list_idx_injection[s_idx]), int(self.list_nmb_stems[s_idx]), compute,
+                              similarity, N)
+        self.shard_stats = sharder.stats
         if self.output_device_frames:
             self.tree_final_imgs = list(self._tree_frames)
         else:

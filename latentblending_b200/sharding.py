@@ -1,0 +1,154 @@
+"""Branch-level sharding of one transition across the GPUs of a node (one process per GPU).
+
+The reference builds the tree strictly sequentially (latentblending/blending_engine.py:354-362):
+each insertion takes the arg-max LPIPS gap, computes the branch at its midpoint and updates the
+two neighbouring similarities, which the NEXT insertion of the same level reads (:541-547 /
+:586-588).  What makes sharding possible is that a branch's latents depend only on its
+``fract_mixing``, the level's ``idx_injection`` and strictly OLDER parents (:549-561, :439-458) --
+never on branches of its own level.  So within a level:
+
+  1. plan:    every rank derives the same list of up to ``world`` candidate midpoints from the
+              replicated tree -- a best-first subdivision of the current gaps (a gap's halves are
+              estimated at half its similarity), skipping midpoints already computed;
+  2. compute: rank r runs candidate r (parental mix + denoise + decode) on its GPU;
+  3. gather:  ONE all-gather per round collects the finished trajectory slabs and decoded frames
+              (``torch.distributed``: NCCL over NVLink on GPUs, gloo in the CPU tests);
+  4. replay:  every rank replays the reference's greedy loop on the replicated tree, consuming
+              cached candidates for as long as the arg-max gap's midpoint has been computed; the
+              first miss starts the next round.  Mis-speculated branches stay cached for later
+              rounds of the level and are dropped at its end.
+
+The tree that results is exactly the sequential one (same ``tree_fracts`` order, same parents):
+the similarity pair of every insertion is taken from rank 0 so all replicas take identical
+decisions.  There is no data-path collective other than the per-round all-gather.
+
+This module is pure host logic + collectives; the arithmetic is injected (``compute``,
+``similarity``), which is how the world_size-2 gloo test drives it on CPU.
+"""
+import heapq
+
+import numpy as np
+import torch
+
+
+def older_parents(tree_fracts, tree_idx_injection, fract, idx_injection):
+    """Indices of the nearest tree nodes left/right of ``fract`` whose idx_injection is older
+    (blending_engine.py:549-561 applied to an arbitrary midpoint)."""
+    fr = np.asarray(tree_fracts)
+    left = int(np.max(np.nonzero(fr <= fract)[0])) if np.any(fr <= fract) else 0
+    # nodes exactly at `fract` cannot exist (midpoints are new); left < right always
+    right = left + 1
+    while tree_idx_injection[left] >= idx_injection:
+        left -= 1
+    while tree_idx_injection[right] >= idx_injection:
+        right += 1
+    return left, right
+
+
+def plan_candidates(tree_fracts, tree_similarities, budget, cached, split_ratio=0.5):
+    """Best-first subdivision of the current gaps -> up to ``budget`` (mid, lo, hi) midpoints not in ``cached``.
+    The first returned candidate is always the reference's next choice (arg-max gap) unless it is cached;
+    the halves of a split gap are estimated at ``split_ratio`` x its similarity."""
+    sims = list(tree_similarities)
+    if len(sims) == 1 and not isinstance(sims[0], (int, float, np.floating)):
+        sims = [1.0]                                  # blending_engine.py:349: first arg-max is over a 1-list
+    heap = []
+    for i, s in enumerate(sims):
+        # ties resolve like np.argmax: lowest index first
+        heapq.heappush(heap, (-float(s), i, 0, float(tree_fracts[i]), float(tree_fracts[i + 1])))
+    out, guard = [], 0
+    while heap and len(out) < budget and guard < 64 * max(1, budget):
+        guard += 1
+        neg, order, depth, lo, hi = heapq.heappop(heap)
+        mid = (lo + hi) / 2
+        if mid not in cached and all(mid != c[0] for c in out):
+            out.append((mid, lo, hi))
+        if depth < 6:
+            heapq.heappush(heap, (neg * split_ratio, order, depth + 1, lo, mid))
+            heapq.heappush(heap, (neg * split_ratio, order, depth + 1, mid, hi))
+    return out
+
+
+class LevelSharder:
+    """Runs the stems of one tree level over ``world`` ranks.
+
+    tree: object with lists tree_fracts, tree_idx_injection, tree_similarities, tree_latents, frames
+          (``frames`` = decoded frames used by ``similarity``) -- replicated on every rank.
+    compute(fract, b_parent1, b_parent2, idx_injection) -> (list_latents, frame)
+    similarity(frame_a, frame_b) -> float
+    """
+
+    def __init__(self, rank, world, group=None, device=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.device = device
+        self.stats = dict(rounds=0, computed=0, used=0)
+        self.split_ratio = 0.6        # running estimate of (similarity of a half) / (similarity of the split gap)
+
+    # -- collectives -------------------------------------------------------------------------
+    def _all_gather(self, t):
+        import torch.distributed as dist
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(outs, t.contiguous(), group=self.group)
+        return outs
+
+    def _bcast_pair(self, a, b):
+        import torch.distributed as dist
+        t = torch.tensor([a, b], dtype=torch.float64, device=self.device if self.device is not None else "cpu")
+        dist.broadcast(t, src=0, group=self.group)
+        return float(t[0]), float(t[1])
+
+    # -- one level ---------------------------------------------------------------------------------
+    def run_level(self, tree, idx_injection, n_stems, compute, similarity, num_steps):
+        cache = {}                # mid -> (list_latents, frame)
+        remaining = int(n_stems)
+        while remaining > 0:
+            cands = plan_candidates(tree.tree_fracts, tree.tree_similarities, self.world, cache, self.split_ratio)
+            self.stats["rounds"] += 1
+            mine = cands[self.rank] if self.rank < len(cands) else None
+            slab = frame = None
+            if mine is not None:
+                p1, p2 = older_parents(tree.tree_fracts, tree.tree_idx_injection, mine[0], idx_injection)
+                traj, frame = compute(mine[0], p1, p2, idx_injection)
+                slab = torch.stack([t.reshape(-1) for t in traj[idx_injection:]], 0)
+            # shapes are identical on every rank that has work; idle ranks send zeros of the same shape
+            ref_shape = self._agree_shapes(slab, frame, tree, idx_injection, num_steps)
+            if slab is None:
+                slab = torch.zeros(ref_shape[0], dtype=ref_shape[2], device=ref_shape[4])
+                frame = torch.zeros(ref_shape[1], dtype=ref_shape[3], device=ref_shape[4])
+            slabs = self._all_gather(slab)
+            frames = self._all_gather(frame)
+            lat_shape = tree.tree_latents[0][-1].shape
+            for r, (mid, lo, hi) in enumerate(cands):
+                traj = [None] * idx_injection + [slabs[r][i].view(lat_shape) for i in range(num_steps - idx_injection)]
+                cache[mid] = (traj, frames[r])
+                self.stats["computed"] += 1
+            # replay the reference's greedy loop on the replicated tree
+            while remaining > 0:
+                sims = tree.tree_similarities
+                c1 = 0 if len(sims) == 1 else int(np.argmax(sims))
+                mid = (tree.tree_fracts[c1] + tree.tree_fracts[c1 + 1]) / 2
+                if mid not in cache:
+                    break
+                traj, frm = cache.pop(mid)
+                left = similarity(frm, tree.frames[c1])
+                right = similarity(frm, tree.frames[c1 + 1])
+                left, right = self._bcast_pair(left, right)
+                parent_sim = sims[c1]
+                if isinstance(parent_sim, (int, float, np.floating)) and parent_sim > 0:
+                    obs = min(1.0, max(left, right) / float(parent_sim))
+                    self.split_ratio = 0.7 * self.split_ratio + 0.3 * obs     # identical on every rank
+                k = c1 + 1
+                tree.tree_latents.insert(k, traj)
+                tree.frames.insert(k, frm)
+                tree.tree_fracts.insert(k, mid)
+                tree.tree_idx_injection.insert(k, idx_injection)
+                tree.tree_similarities[c1] = left
+                tree.tree_similarities.insert(k, right)
+                remaining -= 1
+                self.stats["used"] += 1
+
+    def _agree_shapes(self, slab, frame, tree, idx_injection, num_steps):
+        lat = tree.tree_latents[0][-1]
+        f0 = tree.frames[0]
+        n = lat.numel()
+        return ((num_steps - idx_injection, n), tuple(f0.shape), lat.dtype, f0.dtype, lat.device)
