@@ -30,31 +30,37 @@ struct alignas(64) AttnParams {
 
 namespace {
 
-constexpr int kD = 64, kBQ = 128, kBKV = 128;
-constexpr int kTileBytes = 128 * 64 * 2;      // 16 KiB: Q, K, V tiles
-constexpr int kPBytes = 128 * 128 * 2;        // 32 KiB
-constexpr int kAttnSmem = 3 * kTileBytes + kPBytes + 1024 + 128;
-constexpr int kAttnThreads = 192;
-constexpr uint32_t kTmemCols = 256;           // S: cols [0,128), O_j: cols [128,192)
+constexpr int kD = 64, kBQ = 256, kBKV = 128;   // one CTA: 256 query rows (two 128-row halves), 128-key tiles
+constexpr int kTileBytes = 128 * 64 * 2;        // 16 KiB: one Q half / K / V tile
+constexpr int kPBytes = 128 * 128 * 2;          // 32 KiB: one P tile
+constexpr int kKVStages = 2;
+constexpr int kAttnSmem = (2 + 2 * kKVStages) * kTileBytes + 2 * kPBytes + 1024 + 256;
+constexpr int kAttnThreads = 384;               // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 / 8-11 softmax
+constexpr uint32_t kTmemCols = 512;             // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
 
-__global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+// Pipeline (per CTA, one KV tile j = one "step"):
+//   tensor pipe:  S0[j] S1[j] | PV0[j] S0[j+1] | PV1[j] S1[j+1] | ...
+//   softmax WG0:  -------- softmax(S0[j]) ------ | softmax(S0[j+1]) ...
+//   softmax WG1:       -------- softmax(S1[j]) ------ | ...
+// Each half's softmax overlaps the other half's MMAs; K/V tiles are loaded once per 256 query rows.
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint8_t* sQ = smem;
-    uint8_t* sK = smem + kTileBytes;
-    uint8_t* sV = smem + 2 * kTileBytes;
-    uint8_t* sP = smem + 3 * kTileBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kTileBytes + kPBytes);
+    uint8_t* sQ = smem;                                   // 2 halves
+    uint8_t* sK = sQ + 2 * kTileBytes;                    // kKVStages
+    uint8_t* sV = sK + kKVStages * kTileBytes;            // kKVStages
+    uint8_t* sP = sV + kKVStages * kTileBytes;            // 2 halves
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
     uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;
-    uint64_t* v_full = bars + 2;
-    uint64_t* k_empty = bars + 3;
-    uint64_t* v_empty = bars + 4;
-    uint64_t* s_full = bars + 5;
-    uint64_t* p_ready = bars + 6;
-    uint64_t* o_full = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* k_full = bars + 1;     // [2]
+    uint64_t* k_empty = bars + 3;    // [2]
+    uint64_t* v_full = bars + 5;     // [2]
+    uint64_t* v_empty = bars + 7;    // [2]
+    uint64_t* s_full = bars + 9;     // [2] per half
+    uint64_t* p_ready = bars + 11;   // [2]
+    uint64_t* o_full = bars + 13;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
@@ -65,13 +71,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
         tma_prefetch_desc(&p.tmK);
         tma_prefetch_desc(&p.tmV);
         mbar_init(q_full, 1);
-        mbar_init(k_full, 1);
-        mbar_init(v_full, 1);
-        mbar_init(k_empty, 1);
-        mbar_init(v_empty, 1);
-        mbar_init(s_full, 1);
-        mbar_init(p_ready, 4);
-        mbar_init(o_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_ready[i], 4);
+            mbar_init(&o_full[i], 1);
+        }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -79,53 +87,80 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
 
     if (warp == 0 && lane == 0) {
         // ---------------- TMA producer ----------------
-        mbar_expect_tx(q_full, kTileBytes);
+        mbar_expect_tx(q_full, 2 * kTileBytes);
         tma_load_3d(sQ, &p.tmQ, q_full, p.q_col0 + head * kD, q0, b);
+        tma_load_3d(sQ + kTileBytes, &p.tmQ, q_full, p.q_col0 + head * kD, q0 + 128, b);
         for (int j = 0; j < nkv; ++j) {
-            const uint32_t ph = j & 1;
-            mbar_wait(k_empty, ph ^ 1, p.err_flag, 11);
-            mbar_expect_tx(k_full, kTileBytes);
-            tma_load_3d(sK, &p.tmK, k_full, p.k_col0 + head * kD, j * kBKV, b);
-            mbar_wait(v_empty, ph ^ 1, p.err_flag, 12);
-            mbar_expect_tx(v_full, kTileBytes);
-            tma_load_3d(sV, &p.tmV, v_full, p.v_col0 + head * kD, j * kBKV, b);
+            const int st = j & 1;
+            const uint32_t ph = (j >> 1) & 1;
+            mbar_wait(&k_empty[st], ph ^ 1, p.err_flag, 11);
+            mbar_expect_tx(&k_full[st], kTileBytes);
+            tma_load_3d(sK + st * kTileBytes, &p.tmK, &k_full[st], p.k_col0 + head * kD, j * kBKV, b);
+            mbar_wait(&v_empty[st], ph ^ 1, p.err_flag, 12);
+            mbar_expect_tx(&v_full[st], kTileBytes);
+            tma_load_3d(sV + st * kTileBytes, &p.tmV, &v_full[st], p.v_col0 + head * kD, j * kBKV, b);
         }
     } else if (warp == 1 && lane == 0) {
         // ---------------- MMA issuer ----------------
         constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 0, 0);
         constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, 0, 1);   // B (= V) is MN-major
         const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
-        mbar_wait(q_full, 0, p.err_flag, 13);
-        for (int j = 0; j < nkv; ++j) {
-            const uint32_t ph = j & 1;
-            mbar_wait(k_full, ph, p.err_flag, 14);
-            tc_fence_after();
+        auto issue_qk = [&](int half, int st) {
 #pragma unroll
             for (int k = 0; k < kD / 16; ++k)
-                umma_f16(tmem_S, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                         make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_qk, k != 0);
-            umma_commit(k_empty);
-            umma_commit(s_full);
-            mbar_wait(p_ready, ph, p.err_flag, 15);
-            mbar_wait(v_full, ph, p.err_flag, 16);
-            tc_fence_after();
+                umma_f16(tmem_base + half * 128, make_smem_desc_sw128(q_addr + half * kTileBytes + k * 32, 16, 1024),
+                         make_smem_desc_sw128(k_addr + st * kTileBytes + k * 32, 16, 1024), idesc_qk, k != 0);
+            umma_commit(&s_full[half]);
+        };
+        auto issue_pv = [&](int half, int st) {
 #pragma unroll
             for (int k = 0; k < kBKV / 16; ++k)
-                umma_f16(tmem_O, make_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                         make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, k != 0);
-            umma_commit(v_empty);
-            umma_commit(o_full);
+                umma_f16(tmem_base + 256 + half * 64,
+                         make_smem_desc_sw128(p_addr + half * kPBytes + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                         make_smem_desc_sw128(v_addr + st * kTileBytes + k * 2048, 1024, 1024), idesc_pv, k != 0);
+            umma_commit(&o_full[half]);
+        };
+        mbar_wait(q_full, 0, p.err_flag, 13);
+        mbar_wait(&k_full[0], 0, p.err_flag, 14);
+        tc_fence_after();
+        issue_qk(0, 0);
+        issue_qk(1, 0);
+        umma_commit(&k_empty[0]);
+        for (int j = 0; j < nkv; ++j) {
+            const int st = j & 1, stn = (j + 1) & 1;
+            const uint32_t ph = j & 1, kvph = (j >> 1) & 1, kvphn = ((j + 1) >> 1) & 1;
+            const bool more = j + 1 < nkv;
+            mbar_wait(&v_full[st], kvph, p.err_flag, 16);
+            mbar_wait(&p_ready[0], ph, p.err_flag, 15);
+            tc_fence_after();
+            issue_pv(0, st);
+            if (more) {
+                mbar_wait(&k_full[stn], kvphn, p.err_flag, 14);
+                tc_fence_after();
+                issue_qk(0, stn);
+            }
+            mbar_wait(&p_ready[1], ph, p.err_flag, 15);
+            tc_fence_after();
+            issue_pv(1, st);
+            umma_commit(&v_empty[st]);
+            if (more) {
+                issue_qk(1, stn);
+                umma_commit(&k_empty[stn]);
+            }
         }
-    } else if (warp >= 2) {
-        // ---------------- softmax / output (one query row per thread) ----------------
+    } else if (warp >= 4) {
+        // ---------------- softmax / output: one query row per thread, two independent halves ----------------
+        const int half = (warp - 4) >> 2;
         const int quad = warp & 3;
         const int r = quad * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;
+        const uint32_t tmem_S = tmem_base + half * 128 + lane_off;
+        const uint32_t tmem_O = tmem_base + 256 + half * 64 + lane_off;
+        uint8_t* sPh = sP + half * kPBytes;
+        float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
         float o_acc[kD];
 #pragma unroll
         for (int i = 0; i < kD; ++i) o_acc[i] = 0.f;
@@ -133,29 +168,56 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
         for (int j = 0; j < nkv; ++j) {
             const uint32_t ph = j & 1;
             const int kv_valid = min(kBKV, p.Skv - j * kBKV);
-            mbar_wait(s_full, ph, p.err_flag, 17);
+            mbar_wait(&s_full[half], ph, p.err_flag, 17);
             tc_fence_after();
-            // pass 1: row max
+            // pass 1: row max (3-input max: 64 instructions for 128 values)
             float mx = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
+                tmem_ld_32x32b_x32(tmem_S + c * 32, v);
                 tmem_ld_wait();
+                if (kv_valid == kBKV) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
             }
             const float m_new = fmaxf(m_run, mx * sc);
-            const float alpha = exp2f(m_run - m_new);       // m_run = -inf on the first tile -> 0
-            float psum = 0.f;
-            // pass 2: p = 2^(s*sc - m_new) -> fp16 -> smem (K-major, 128B swizzle: chunk ^= row & 7)
+            const float alpha = ex2_approx(m_run - m_new);   // first tile: 2^(-inf) = 0
+            // fold the PREVIOUS tile's P V into the running output while this tile's MMAs are in flight
+            if (j > 0) {
+                mbar_wait(&o_full[half], ph ^ 1, p.err_flag, 18);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_O + c * 32, v);
+                    tmem_ld_wait();
+                    const float2 a2 = make_float2(alpha_prev, alpha_prev);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float2 r2 = ffma2(make_float2(o_acc[c * 32 + i], o_acc[c * 32 + i + 1]), a2,
+                                                make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                        o_acc[c * 32 + i] = r2.x;
+                        o_acc[c * 32 + i + 1] = r2.y;
+                    }
+                }
+            }
+            alpha_prev = alpha;
+            float2 psum2 = make_float2(0.f, 0.f);
+            const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_new, -m_new);
+            // pass 2: p = 2^(s*sc - m_new) -> fp16 -> smem (K-major, 128B swizzle: 16B chunk ^= row & 7).
+            // Packed fp32 FMAs; every 4th pair takes the polynomial 2^x so MUFU.EX2 (16/clk/SM) is not the only exp unit.
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, v);
+                tmem_ld_32x32b_x32(tmem_S + c * 32, v);
                 tmem_ld_wait();
-                uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
+                uint8_t* prow = sPh + (c >> 1) * 16384 + r * 128;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint4 pk;
@@ -163,38 +225,48 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int col = c * 32 + g * 8 + 2 * i;
-                        float e0 = (col < kv_valid) ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * i]), sc, -m_new)) : 0.f;
-                        float e1 = (col + 1 < kv_valid) ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * i + 1]), sc, -m_new)) : 0.f;
-                        __half2 h2 = __floats2half2_rn(e0, e1);
-                        // accumulate the row sum from the ROUNDED probabilities (what the PV MMA sees)
-                        float2 back = __half22float2(h2);
-                        psum += back.x + back.y;
-                        ph2[i] = h2;
+                        const float2 x2 = ffma2(make_float2(__uint_as_float(v[g * 8 + 2 * i]),
+                                                            __uint_as_float(v[g * 8 + 2 * i + 1])), sc2, nm2);
+                        float2 e2;
+                        if (i == 3) {
+                            e2.x = ex2_poly(x2.x);
+                            e2.y = ex2_poly(x2.y);
+                        } else {
+                            e2.x = ex2_approx(x2.x);
+                            e2.y = ex2_approx(x2.y);
+                        }
+                        if (kv_valid != kBKV) {
+                            if (col >= kv_valid) e2.x = 0.f;
+                            if (col + 1 >= kv_valid) e2.y = 0.f;
+                        }
+                        psum2 = fadd2(psum2, e2);
+                        ph2[i] = __floats2half2_rn(e2.x, e2.y);
                     }
                     const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
                     *reinterpret_cast<uint4*>(prow + chunk * 16) = pk;
                 }
             }
+            const float psum = psum2.x + psum2.y;
             l_run = l_run * alpha + psum;
             m_run = m_new;
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_ready);
-            // O = alpha * O + P V
-            mbar_wait(o_full, ph, p.err_flag, 18);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(v[i]));
-            }
-            tc_fence_before();
+            if (lane == 0) mbar_arrive(&p_ready[half]);
         }
-        const int q = q0 + r;
+        // last tile's P V
+        mbar_wait(&o_full[half], (nkv - 1) & 1, p.err_flag, 19);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_O + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
+        }
+        tc_fence_before();
+        const int q = q0 + half * 128 + r;
         if (q < p.Sq) {
             const float inv = 1.0f / l_run;
             __half* dst = p.out + ((long long)b * p.Sq + q) * p.ldo + head * kD;
