@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
     uint64_t* o_full = bars + 13;    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
     const int nkv = (p.Skv + kBKV - 1) / kBKV;
 
@@ -88,47 +88,63 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
-        // ---------------- TMA producer ----------------
-        mbar_expect_tx(q_full, 2 * kTileBytes);
-        tma_load_3d(sQ, &p.tmQ, q_full, p.q_col0 + head * kD, q0, b);
-        tma_load_3d(sQ + kTileBytes, &p.tmQ, q_full, p.q_col0 + head * kD, q0 + 128, b);
+    if (warp == 0) {
+        // ---------------- TMA producer (warp-uniform loop, one elected lane issues) ----------------
+        if (elect_one()) {
+            mbar_expect_tx(q_full, 2 * kTileBytes);
+            tma_load_3d(sQ, &p.tmQ, q_full, p.q_col0 + head * kD, q0, b);
+            tma_load_3d(sQ + kTileBytes, &p.tmQ, q_full, p.q_col0 + head * kD, q0 + 128, b);
+        }
+        __syncwarp();
         for (int j = 0; j < nkv; ++j) {
             const int st = j & 1;
             const uint32_t ph = (j >> 1) & 1;
             mbar_wait(&k_empty[st], ph ^ 1, p.err_flag, 11);
-            mbar_expect_tx(&k_full[st], kTileBytes);
-            tma_load_3d(sK + st * kTileBytes, &p.tmK, &k_full[st], p.k_col0 + head * kD, j * kBKV, b);
+            if (elect_one()) {
+                mbar_expect_tx(&k_full[st], kTileBytes);
+                tma_load_3d(sK + st * kTileBytes, &p.tmK, &k_full[st], p.k_col0 + head * kD, j * kBKV, b);
+            }
+            __syncwarp();
             mbar_wait(&v_empty[st], ph ^ 1, p.err_flag, 12);
-            mbar_expect_tx(&v_full[st], kTileBytes);
-            tma_load_3d(sV + st * kTileBytes, &p.tmV, &v_full[st], p.v_col0 + head * kD, j * kBKV, b);
+            if (elect_one()) {
+                mbar_expect_tx(&v_full[st], kTileBytes);
+                tma_load_3d(sV + st * kTileBytes, &p.tmV, &v_full[st], p.v_col0 + head * kD, j * kBKV, b);
+            }
+            __syncwarp();
         }
-    } else if (warp == 1 && lane == 0) {
-        // ---------------- MMA issuer ----------------
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (warp-uniform loop, one elected lane issues) ----------------
         constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 0, 0);
         constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, 0, 1);   // B (= V) is MN-major
         const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
-        auto issue_qk = [&](int half, int st) {
+        auto issue_qk = [&](int half, int st, uint64_t* also_commit) {
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kD / 16; ++k)
-                umma_f16(tmem_base + half * 128, make_smem_desc_sw128(q_addr + half * kTileBytes + k * 32, 16, 1024),
-                         make_smem_desc_sw128(k_addr + st * kTileBytes + k * 32, 16, 1024), idesc_qk, k != 0);
-            umma_commit(&s_full[half]);
+                for (int k = 0; k < kD / 16; ++k)
+                    umma_f16(tmem_base + half * 128, make_smem_desc_sw128(q_addr + half * kTileBytes + k * 32, 16, 1024),
+                             make_smem_desc_sw128(k_addr + st * kTileBytes + k * 32, 16, 1024), idesc_qk, k != 0);
+                umma_commit(&s_full[half]);
+                if (also_commit) umma_commit(also_commit);
+            }
+            __syncwarp();
         };
-        auto issue_pv = [&](int half, int st) {
+        auto issue_pv = [&](int half, int st, uint64_t* also_commit) {
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBKV / 16; ++k)
-                umma_f16(tmem_base + 256 + half * 64,
-                         make_smem_desc_sw128(p_addr + half * kPBytes + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                         make_smem_desc_sw128(v_addr + st * kTileBytes + k * 2048, 1024, 1024), idesc_pv, k != 0);
-            umma_commit(&o_full[half]);
+                for (int k = 0; k < kBKV / 16; ++k)
+                    umma_f16(tmem_base + 256 + half * 64,
+                             make_smem_desc_sw128(p_addr + half * kPBytes + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                             make_smem_desc_sw128(v_addr + st * kTileBytes + k * 2048, 1024, 1024), idesc_pv, k != 0);
+                umma_commit(&o_full[half]);
+                if (also_commit) umma_commit(also_commit);
+            }
+            __syncwarp();
         };
         mbar_wait(q_full, 0, p.err_flag, 13);
         mbar_wait(&k_full[0], 0, p.err_flag, 14);
         tc_fence_after();
-        issue_qk(0, 0);
-        issue_qk(1, 0);
-        umma_commit(&k_empty[0]);
+        issue_qk(0, 0, nullptr);
+        issue_qk(1, 0, &k_empty[0]);
         for (int j = 0; j < nkv; ++j) {
             const int st = j & 1, stn = (j + 1) & 1;
             const uint32_t ph = j & 1, kvph = (j >> 1) & 1, kvphn = ((j + 1) >> 1) & 1;
@@ -136,20 +152,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
             mbar_wait(&v_full[st], kvph, p.err_flag, 16);
             mbar_wait(&p_ready[0], ph, p.err_flag, 15);
             tc_fence_after();
-            issue_pv(0, st);
+            issue_pv(0, st, nullptr);
             if (more) {
                 mbar_wait(&k_full[stn], kvphn, p.err_flag, 14);
                 tc_fence_after();
-                issue_qk(0, stn);
+                issue_qk(0, stn, nullptr);
             }
             mbar_wait(&p_ready[1], ph, p.err_flag, 15);
             tc_fence_after();
-            issue_pv(1, st);
-            umma_commit(&v_empty[st]);
-            if (more) {
-                issue_qk(1, stn);
-                umma_commit(&k_empty[stn]);
-            }
+            issue_pv(1, st, &v_empty[st]);
+            if (more) issue_qk(1, stn, &k_empty[stn]);
         }
     } else if (warp >= 4) {
         // ---------------- softmax / output: one query row per thread, two independent halves ----------------

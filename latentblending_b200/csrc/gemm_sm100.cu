@@ -21,6 +21,8 @@
 //              double-buffered accumulators overlap it with the next tile's MMAs
 // Bound: tensor pipe; algorithmic FLOPs = 2*M*N*K.
 #include "gemm_sm100.cuh"
+#include <stdlib.h>
+
 #include "sm100.cuh"
 
 using namespace sm100;
@@ -39,6 +41,7 @@ template <int BN> struct Cfg {
     static constexpr int tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
     static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int pair_stage_bytes = kABytes + b_bytes / 2;   // bytes ONE CTA of a pair stages per k-block
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -53,9 +56,14 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     }
 }
 
-template <int BN>
+// CL = 2 (cta_group::2): a CTA PAIR owns a 256 x BN tile -- two vertically adjacent 128-row M tiles of one N tile.
+// Each CTA stages its own A tile and HALF of the weight tile; the leader issues tcgen05.mma.cta_group::2 (M = 256),
+// each SM's tensor core accumulates its 128 rows in its own TMEM and the weight halves are shared across the pair,
+// so per-SM shared-memory traffic (the limiter of single-CTA M=128 MMAs on Blackwell) drops by BN/2 rows per k-block.
+template <int BN, int CL>
 __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     using C = Cfg<BN>;
+    const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
@@ -68,7 +76,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA[0]);
@@ -80,48 +88,70 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);
+            mbar_init(&tmem_empty[a], 4 * CL);   // pair: the leader waits for both CTAs' epilogue warps
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, C::tmem_cols);
+    if (warp == 2) {
+        if (CL == 2) tmem_alloc_2sm(tmem_slot, C::tmem_cols);
+        else tmem_alloc(tmem_slot, C::tmem_cols);
+    }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();          // peer barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    // tile index space: (m-group, n) with CL vertically adjacent M tiles per group
+    const int m_groups = (p.tiles_m + CL - 1) / CL;
+    const int num_tiles = m_groups * p.tiles_n;
+    const int tile0 = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-    if (warp == 0 && lane == 0) {
-        // ===================== TMA producer =====================
+    if (warp == 0) {
+        // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_tile = tile % p.tiles_m, n_tile = tile / p.tiles_m;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            const int m_tile = (tile % m_groups) * CL + (int)crank, n_tile = tile / m_groups;
             const int x0 = (m_tile % p.tiles_x) * p.tw;
             const int y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.th;
-            const int b0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.tb;
+            const int b0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.tb;   // m_tile == tiles_m (odd tail): fully OOB -> zeros
             int kb_global = 0;
             for (int s = 0; s < p.num_segs; ++s) {
                 const CUtensorMap* ma = &p.tmA[p.seg_map[s]];
                 const int dy = p.seg_dy[s], dx = p.seg_dx[s];
                 for (int kb = 0; kb < p.seg_kb[s]; ++kb, ++kb_global) {
                     mbar_wait(&empty[stage], phase ^ 1, p.err_flag, 1);
-                    mbar_expect_tx(&full[stage], C::stage_bytes);
-                    tma_load_4d(smem_a + stage * kABytes, ma, &full[stage], kb * kBK, x0 + dx, y0 + dy, b0);
-                    tma_load_2d(smem_b + stage * C::b_bytes, &p.tmB, &full[stage], kb_global * kBK, n_tile * BN);
+                    if (elect_one()) {
+                    if (p.debug & 1) {                 // profiling: no data movement, just hand the slot over
+                        if (CL == 1 || crank == 0) mbar_arrive(&full[stage]);
+                    } else if (CL == 2) {
+                        // both CTAs' bytes are counted on the LEADER's full barrier
+                        const uint32_t lead_full = map_to_cta(&full[stage], 0);
+                        if (crank == 0) mbar_expect_tx(&full[stage], 2 * C::pair_stage_bytes);
+                        tma_load_4d_2sm(smem_a + stage * kABytes, ma, lead_full, kb * kBK, x0 + dx, y0 + dy, b0);
+                        tma_load_2d_2sm(smem_b + stage * C::b_bytes, &p.tmBh, lead_full, kb_global * kBK,
+                                        n_tile * BN + (int)crank * (BN / 2));
+                    } else {
+                        mbar_expect_tx(&full[stage], C::stage_bytes);
+                        tma_load_4d(smem_a + stage * kABytes, ma, &full[stage], kb * kBK, x0 + dx, y0 + dy, b0);
+                        tma_load_2d(smem_b + stage * C::b_bytes, &p.tmB, &full[stage], kb_global * kBK, n_tile * BN);
+                    }
+                    }
+                    __syncwarp();
                     if (++stage == C::stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_f16(kBM, BN);
+    } else if (warp == 1 && crank == 0) {
+        // ===================== MMA issuer (pair: leader CTA only) =====================
+        constexpr uint32_t idesc = make_idesc_f16(kBM * CL, BN);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.err_flag, 2);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
@@ -130,16 +160,26 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
                 const uint32_t b_addr = smem_u32(smem_b + stage * C::b_bytes);
+                if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
                     const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
                     const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                    umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+                    if (p.debug & 2) continue;         // profiling: no tensor work
+                    if (CL == 2) umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+                    else umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
                 }
-                umma_commit(&empty[stage]);
+                if (CL == 2) umma_commit_2sm(&empty[stage], (uint16_t)0x3);   // frees the slot in both CTAs
+                else umma_commit(&empty[stage]);
+                }
+                __syncwarp();
                 if (++stage == C::stages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&tmem_full[acc]);
+            if (elect_one()) {
+                if (CL == 2) umma_commit_2sm(&tmem_full[acc], (uint16_t)0x3);
+                else umma_commit(&tmem_full[acc]);
+            }
+            __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 2) {
@@ -149,12 +189,12 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
         const int ww = r % p.tw, hh = (r / p.tw) % p.th, bb = r / (p.tw * p.th);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_tile = tile % p.tiles_m, n_tile = tile / p.tiles_m;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            const int m_tile = (tile % m_groups) * CL + (int)crank, n_tile = tile / m_groups;
             const int x = (m_tile % p.tiles_x) * p.tw + ww;
             const int y = ((m_tile / p.tiles_x) % p.tiles_y) * p.th + hh;
             const int b = (m_tile / (p.tiles_x * p.tiles_y)) * p.tb + bb;
-            const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B);
+            const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B) && (m_tile < p.tiles_m);
             const long long row = ((long long)b * p.H + y) * p.W + x;
             mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 4);
             tc_fence_after();
@@ -243,14 +283,21 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (CL == 2) mbar_arrive_cluster(map_to_cta(&tmem_empty[acc], 0));
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, C::tmem_cols);
+    if (CL == 2) cluster_sync_all();          // the peer may still arrive on this CTA's barriers / read its smem
+    if (warp == 2) {
+        if (CL == 2) tmem_dealloc_2sm(tmem_base, C::tmem_cols);
+        else tmem_dealloc(tmem_base, C::tmem_cols);
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------
@@ -309,16 +356,30 @@ int encode_weight_map(lb_ctx* ctx, CUtensorMap* m, const void* base, int64_t ld,
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-template <int BN> int launch_bn(const GemmPlan& plan, cudaStream_t st) {
+template <int BN, int CL> int launch_bn_cl(const GemmPlan& plan, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<BN>::smem_bytes));
         attr_set = true;
     }
-    gemm_tc_kernel<BN><<<plan.grid, kThreadsGemm, Cfg<BN>::smem_bytes, st>>>(plan.p);
-    LB_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)plan.grid);
+    cfg.blockDim = dim3(kThreadsGemm);
+    cfg.dynamicSmemBytes = Cfg<BN>::smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, plan.p));
     return 0;
+}
+template <int BN> int launch_bn(const GemmPlan& plan, cudaStream_t st) {
+    return plan.cluster == 2 ? launch_bn_cl<BN, 2>(plan, st) : launch_bn_cl<BN, 1>(plan, st);
 }
 
 }  // namespace
@@ -397,6 +458,7 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
         p.tmA[1] = p.tmA[0];
     }
     if (int e = encode_weight_map(ctx, &p.tmB, d.w, d.w_ld, Ktot, d.N, bn)) return e;
+    if (int e = encode_weight_map(ctx, &p.tmBh, d.w, d.w_ld, Ktot, d.N, bn / 2)) return e;
     p.out = static_cast<__half*>(d.out);
     p.ldo = d.out_ld;
     p.bias = static_cast<const __half*>(d.bias);
@@ -405,8 +467,21 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
     p.res = static_cast<const __half*>(d.res);
     p.ldr = d.res_ld;
     p.err_flag = lb_err_flag(ctx);
-    const int tiles = p.tiles_m * p.tiles_n;
-    plan->grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    p.debug = getenv("LB_GEMM_DEBUG") ? atoi(getenv("LB_GEMM_DEBUG")) : 0;
+    // CTA pairs (cta_group::2, M = 256) whenever there are at least two M tiles
+    // (measured: the pair wins ~3 % on long-K multi-wave problems -- the big convolutions -- and loses up to 15 %
+    //  on short-K / single-wave ones, where its cluster launch + sync overhead dominates)
+    const char* force = getenv("LB_GEMM_CLUSTER");
+    plan->cluster = (p.tiles_m >= 2 && total >= 40 && (int64_t)p.tiles_m * p.tiles_n >= 256) ? 2 : 1;
+    if (force) plan->cluster = (atoi(force) == 2 && p.tiles_m >= 2) ? 2 : 1;
+    if (plan->cluster == 2) {
+        const int groups = ((p.tiles_m + 1) / 2) * p.tiles_n;
+        const int max_groups = ctx->sm_count / 2;
+        plan->grid = 2 * (groups < max_groups ? groups : max_groups);
+    } else {
+        const int tiles = p.tiles_m * p.tiles_n;
+        plan->grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    }
     plan->smem_bytes = 0;
     return 0;
 }

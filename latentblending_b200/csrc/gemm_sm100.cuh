@@ -22,6 +22,7 @@ constexpr int kGemmMaxSegs = 12;
 struct alignas(64) GemmParams {
     CUtensorMap tmA[2];
     CUtensorMap tmB;
+    CUtensorMap tmBh;      // half-height box (BN/2 rows) for the 2-CTA multicast variant
     int num_segs;
     int seg_map[kGemmMaxSegs], seg_dy[kGemmMaxSegs], seg_dx[kGemmMaxSegs], seg_kb[kGemmMaxSegs];
     int total_kb;
@@ -35,6 +36,7 @@ struct alignas(64) GemmParams {
     const __half* bias2; long long bias2_ld;
     const __half* res; long long ldr;
     int* err_flag;
+    int debug;     // profiling knobs (LB_GEMM_DEBUG): 1 = skip TMA issue, 2 = skip MMA issue
 };
 
 struct GemmPlan {
@@ -42,6 +44,7 @@ struct GemmPlan {
     int bn;        // N tile: 64 / 128 / 160 / 256
     int grid;
     int smem_bytes;
+    int cluster;   // 1, or 2 = CTA pairs along M sharing the weight tile via TMA multicast
 };
 
 int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan);
