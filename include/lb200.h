@@ -170,6 +170,19 @@ int lb_upsample2x(lb_ctx* ctx, const void* x, int64_t ld, int B, int H, int W, i
                   void* stream);
 int lb_im2col_s2(lb_ctx* ctx, const void* x, int64_t ld, int B, int H, int W, int C, void* out, void* stream);
 
+/* ---- VAE decoder helpers (latent2image, diffusers_holder.py:114-143) ----
+ * lb_latent_prep: post_quant_conv(latents / scaling_factor) as a per-pixel CxC fp32 matrix (scale folded in).
+ * lb_softmax_rows: row softmax of an fp16 matrix (the VAE mid-block single-head attention, head dim 512,
+ *   runs as lb_gemm(Q,K) -> lb_softmax_rows -> lb_gemm(P,V^T)).
+ * lb_postprocess_u8: (x/2+0.5).clamp(0,1)*255 -> uint8 NHWC (VaeImageProcessor.postprocess).
+ */
+int lb_latent_prep(lb_ctx* ctx, const void* x_nchw, int B, int C, int64_t hw, const void* w_f32,
+                   const void* bias_f32, void* out_nchw, void* stream);
+int lb_softmax_rows(lb_ctx* ctx, const void* x, int64_t ld, int64_t rows, int cols, void* out, int64_t ldo,
+                    void* stream);
+int lb_postprocess_u8(lb_ctx* ctx, const void* img_nchw, int B, int C, int64_t hw, void* out_u8_nhwc,
+                      void* stream);
+
 /* ---- UNet executor ---------------------------------------------------------------
  * A program is a flat list of the ops above over static device buffers (one
  * SDXL UNet forward for a fixed batch/height/width lowers to ~1.7k records).
@@ -180,7 +193,8 @@ int lb_im2col_s2(lb_ctx* ctx, const void* x, int64_t ld, int B, int H, int W, in
  */
 enum {
     LB_OP_GEMM = 1, LB_OP_ATTENTION = 2, LB_OP_GROUPNORM = 3, LB_OP_LAYERNORM = 4, LB_OP_EMBED_INPUTS = 5,
-    LB_OP_LINEAR_SMALL = 6, LB_OP_CONV_IN = 7, LB_OP_CONV_OUT = 8, LB_OP_UPSAMPLE2X = 9, LB_OP_IM2COL_S2 = 10
+    LB_OP_LINEAR_SMALL = 6, LB_OP_CONV_IN = 7, LB_OP_CONV_OUT = 8, LB_OP_UPSAMPLE2X = 9, LB_OP_IM2COL_S2 = 10,
+    LB_OP_LATENT_PREP = 11, LB_OP_SOFTMAX_ROWS = 12, LB_OP_POSTPROCESS_U8 = 13
 };
 typedef struct lb_op {
     int32_t kind;
@@ -198,6 +212,9 @@ typedef struct lb_op {
         struct { const void* x; int64_t ld_x; int32_t B, Cin, H, W; const void* w; const void* bias;
                  int32_t Cout; void* out; int64_t ld_out; } conv;
         struct { const void* x; int64_t ld_x; int32_t B, H, W, C; void* out; int64_t ld_out; } resample;
+        /* LATENT_PREP: x,w,bias,out,B,C,n=h*w; SOFTMAX_ROWS: x,ld_x,out,ld_out,n=rows,C=cols; POSTPROCESS_U8: x,out,B,C,n=h*w */
+        struct { const void* x; int64_t ld_x; const void* w; const void* bias; void* out; int64_t ld_out;
+                 int64_t n; int32_t B, C; } aux;
     } u;
 } lb_op;
 typedef struct lb_program lb_program;

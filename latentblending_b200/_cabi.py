@@ -70,9 +70,14 @@ class _ResampleOp(ctypes.Structure):
                 ("out", c_void_p), ("ld_out", c_int64)]
 
 
+class _AuxOp(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("ld_x", c_int64), ("w", c_void_p), ("bias", c_void_p), ("out", c_void_p),
+                ("ld_out", c_int64), ("n", c_int64), ("B", c_int32), ("C", c_int32)]
+
+
 class _OpUnion(ctypes.Union):
     _fields_ = [("gemm", GemmDesc), ("attn", AttnDesc), ("norm", _NormOp), ("embed", _EmbedOp), ("lin", _LinOp),
-                ("conv", _ConvOp), ("resample", _ResampleOp)]
+                ("conv", _ConvOp), ("resample", _ResampleOp), ("aux", _AuxOp)]
 
 
 class Op(ctypes.Structure):
@@ -81,7 +86,7 @@ class Op(ctypes.Structure):
 
 
 (OP_GEMM, OP_ATTENTION, OP_GROUPNORM, OP_LAYERNORM, OP_EMBED_INPUTS, OP_LINEAR_SMALL, OP_CONV_IN, OP_CONV_OUT,
- OP_UPSAMPLE2X, OP_IM2COL_S2) = range(1, 11)
+ OP_UPSAMPLE2X, OP_IM2COL_S2, OP_LATENT_PREP, OP_SOFTMAX_ROWS, OP_POSTPROCESS_U8) = range(1, 14)
 
 
 # name -> (restype, argtypes); mirrors include/lb200.h one to one
@@ -122,6 +127,9 @@ SIGNATURES = {
                             c_void_p, c_void_p]),
     "lb_upsample2x": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "lb_im2col_s2": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "lb_latent_prep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lb_softmax_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "lb_postprocess_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -341,3 +341,133 @@ extern "C" int lb_im2col_s2(lb_ctx* ctx, const void* x, int64_t ld, int B, int H
     LB_LAUNCH_CHECK();
     return 0;
 }
+
+// ======================= VAE-decoder helpers (SURVEY section 8f "next #1") ==========================================
+// latent_prep: z = post_quant_conv(latents / scaling_factor), a per-pixel CxC matrix (diffusers_holder.py:135,
+// AutoencoderKL.decode); NCHW fp16 in/out, the 1/scaling_factor is folded into w on the host.
+namespace {
+__global__ void __launch_bounds__(kThreads)
+latent_prep_kernel(const __half* __restrict__ x, int B, int C, long long hw, const float* __restrict__ w /*[C][C]*/,
+                   const float* __restrict__ bias, __half* __restrict__ out) {
+    const long long total = (long long)B * hw;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const long long b = i / hw, p = i % hw;
+        float in[8];
+        for (int c = 0; c < C; ++c) in[c] = __half2float(x[(b * C + c) * hw + p]);
+        for (int o = 0; o < C; ++o) {
+            float acc = bias[o];
+            for (int c = 0; c < C; ++c) acc = fmaf(w[o * C + c], in[c], acc);
+            out[(b * C + o) * hw + p] = __float2half_rn(acc);
+        }
+    }
+}
+
+// row softmax (in place capable): out[r,:] = softmax(x[r,:]) over `cols` fp16 values, one CTA per row.
+__global__ void __launch_bounds__(kThreads)
+softmax_rows_kernel(const __half* __restrict__ x, long long ld, int cols, __half* __restrict__ out, long long ldo) {
+    const long long r = blockIdx.x;
+    const __half* xr = x + r * ld;
+    __half* orow = out + r * ldo;
+    __shared__ float red[kThreads / 32];
+    __shared__ float bc;
+    const int vecs = cols >> 3;
+    float mx = -INFINITY;
+    for (int v = threadIdx.x; v < vecs; v += kThreads) {
+        const uint4 q = *reinterpret_cast<const uint4*>(xr + v * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            mx = fmaxf(mx, fmaxf(f.x, f.y));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = red[0];
+        for (int i = 1; i < kThreads / 32; ++i) m = fmaxf(m, red[i]);
+        bc = m;
+    }
+    __syncthreads();
+    mx = bc;
+    float sum = 0.f;
+    for (int v = threadIdx.x; v < vecs; v += kThreads) {
+        const uint4 q = *reinterpret_cast<const uint4*>(xr + v * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            sum += __expf(f.x - mx) + __expf(f.y - mx);
+        }
+    }
+    sum = lb_warp_sum(sum);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < kThreads / 32; ++i) s += red[i];
+        bc = 1.0f / s;
+    }
+    __syncthreads();
+    const float inv = bc;
+    for (int v = threadIdx.x; v < vecs; v += kThreads) {
+        const uint4 q = *reinterpret_cast<const uint4*>(xr + v * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            oh[j] = __floats2half2_rn(__expf(f.x - mx) * inv, __expf(f.y - mx) * inv);
+        }
+        *reinterpret_cast<uint4*>(orow + v * 8) = o;
+    }
+}
+
+// VaeImageProcessor.postprocess: NCHW fp16 image -> uint8 NHWC, (x/2+0.5).clamp(0,1)*255 rounded half-to-even
+__global__ void __launch_bounds__(kThreads)
+postprocess_u8_kernel(const __half* __restrict__ img, int B, int C, long long hw, uint8_t* __restrict__ out) {
+    const long long total = (long long)B * hw * C;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const int c = (int)(i % C);
+        const long long p = (i / C) % hw, b = i / (C * hw);
+        float v = __half2float(img[(b * C + c) * hw + p]) / 2.0f + 0.5f;
+        v = fminf(fmaxf(v, 0.f), 1.f);
+        out[i] = (uint8_t)__float2int_rn(v * 255.0f);
+    }
+}
+}  // namespace
+
+extern "C" int lb_latent_prep(lb_ctx* ctx, const void* x_nchw, int B, int C, int64_t hw, const void* w_f32,
+                              const void* bias_f32, void* out_nchw, void* stream) {
+    LB_REQUIRE(ctx && x_nchw && w_f32 && bias_f32 && out_nchw, "lb_latent_prep: null argument");
+    LB_REQUIRE(C >= 1 && C <= 8, "lb_latent_prep: C must be <= 8");
+    latent_prep_kernel<<<grid_for((long long)B * hw, ctx->sm_count), kThreads, 0, lb_stream(stream)>>>(
+        (const __half*)x_nchw, B, C, hw, (const float*)w_f32, (const float*)bias_f32, (__half*)out_nchw);
+    LB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lb_softmax_rows(lb_ctx* ctx, const void* x, int64_t ld, int64_t rows, int cols, void* out, int64_t ldo,
+                               void* stream) {
+    LB_REQUIRE(ctx && x && out, "lb_softmax_rows: null argument");
+    LB_REQUIRE(cols % 8 == 0 && ld % 8 == 0 && ldo % 8 == 0 && lb_aligned16(x) && lb_aligned16(out),
+               "lb_softmax_rows: cols / strides must be multiples of 8, bases 16B aligned");
+    LB_REQUIRE(rows <= 2147483647LL, "lb_softmax_rows: too many rows");
+    if (rows == 0) return 0;
+    softmax_rows_kernel<<<(unsigned)rows, kThreads, 0, lb_stream(stream)>>>((const __half*)x, ld, cols, (__half*)out, ldo);
+    LB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lb_postprocess_u8(lb_ctx* ctx, const void* img_nchw, int B, int C, int64_t hw, void* out_u8_nhwc,
+                                 void* stream) {
+    LB_REQUIRE(ctx && img_nchw && out_u8_nhwc, "lb_postprocess_u8: null argument");
+    postprocess_u8_kernel<<<grid_for((long long)B * hw * C, ctx->sm_count), kThreads, 0, lb_stream(stream)>>>(
+        (const __half*)img_nchw, B, C, hw, (uint8_t*)out_u8_nhwc);
+    LB_LAUNCH_CHECK();
+    return 0;
+}

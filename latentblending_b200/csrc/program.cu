@@ -43,6 +43,7 @@ extern "C" int lb_program_create(lb_ctx* ctx, const lb_op* ops, int64_t n_ops, l
                 break;
             case LB_OP_EMBED_INPUTS: case LB_OP_LINEAR_SMALL: case LB_OP_CONV_IN: case LB_OP_CONV_OUT:
             case LB_OP_UPSAMPLE2X: case LB_OP_IM2COL_S2: case LB_OP_GROUPNORM: case LB_OP_LAYERNORM:
+            case LB_OP_LATENT_PREP: case LB_OP_SOFTMAX_ROWS: case LB_OP_POSTPROCESS_U8:
                 break;
             default:
                 lb_set_error("lb_program_create: op %lld has unknown kind %d", (long long)i, ops[i].kind);
@@ -141,6 +142,21 @@ extern "C" int lb_program_run_kinds(lb_program* prog, float t, uint32_t kind_mas
             case LB_OP_LAYERNORM: {
                 const auto& a = o.u.norm;
                 e = lb_layernorm(ctx, a.x, a.ld_x, a.rows, a.C, a.gamma, a.beta, a.eps, a.out, a.ld_out, stream);
+                break;
+            }
+            case LB_OP_LATENT_PREP: {
+                const auto& a = o.u.aux;
+                e = lb_latent_prep(ctx, a.x, a.B, a.C, a.n, a.w, a.bias, a.out, stream);
+                break;
+            }
+            case LB_OP_SOFTMAX_ROWS: {
+                const auto& a = o.u.aux;
+                e = lb_softmax_rows(ctx, a.x, a.ld_x, a.n, a.C, a.out, a.ld_out, stream);
+                break;
+            }
+            case LB_OP_POSTPROCESS_U8: {
+                const auto& a = o.u.aux;
+                e = lb_postprocess_u8(ctx, a.x, a.B, a.C, a.n, a.out, stream);
                 break;
             }
         }

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .next_rows import TorchVAEDecoder, postprocess_uint8
+from .vae import VAEDecoderB200
 from .unet import UNetB200
 
 
@@ -41,8 +41,7 @@ class DiffusersHolder:
         self.width_latent = self.height_latent = s
         self.width_img = self.height_img = s * pipe.vae_scale_factor
         self.unet = UNetB200(pipe.unet_cfg, pipe.unet_state_dict, self.device)
-        self.vae = TorchVAEDecoder(pipe.vae_state_dict, self.device, n_up_blocks=len(pipe.vae_channels),
-                                   scaling_factor=pipe.vae_scaling_factor)
+        self.vae = VAEDecoderB200(pipe.vae_state_dict, pipe.vae_channels, pipe.vae_scaling_factor, self.device)
         self.noise_fn = None          # tests: inject the ancestral-step noise, noise_fn(i, shape)
         self._cond_key = None
         self.n_unet_calls = 0
@@ -84,7 +83,7 @@ class DiffusersHolder:
     @torch.no_grad()
     def decode_to_device(self, latents):
         """latents [1,4,h,w] -> uint8 [H,W,3] frame on the device."""
-        return postprocess_uint8(self.vae.decode(latents))[0]
+        return self.vae.decode_to_u8(latents.to(torch.float16))
 
     @torch.no_grad()
     def latent2image(self, latents, output_type="pil"):

@@ -27,7 +27,8 @@ import torch
 
 from . import _cabi
 from ._cabi import (OP_ATTENTION, OP_CONV_IN, OP_CONV_OUT, OP_EMBED_INPUTS, OP_GEMM, OP_GROUPNORM, OP_IM2COL_S2,
-                    OP_LAYERNORM, OP_LINEAR_SMALL, OP_UPSAMPLE2X, Op, check, ctx, stream_ptr)
+                    OP_LATENT_PREP, OP_LAYERNORM, OP_LINEAR_SMALL, OP_POSTPROCESS_U8, OP_SOFTMAX_ROWS, OP_UPSAMPLE2X,
+                    Op, check, ctx, stream_ptr)
 
 
 @dataclass
@@ -152,6 +153,23 @@ class Program:
         d = self._new(OP_IM2COL_S2).u.resample
         d.x, d.ld_x, d.B, d.H, d.W, d.C, d.out, d.ld_out = _p(x), x.stride(0), B, H, W, C, _p(out), out.stride(0)
         self.hold(x, out)
+
+    def latent_prep(self, x_nchw, w_f32, bias_f32, out_nchw):
+        d = self._new(OP_LATENT_PREP).u.aux
+        B, C, H, W = x_nchw.shape
+        d.x, d.w, d.bias, d.out, d.n, d.B, d.C = _p(x_nchw), _p(w_f32), _p(bias_f32), _p(out_nchw), H * W, B, C
+        self.hold(x_nchw, w_f32, bias_f32, out_nchw)
+
+    def softmax_rows(self, x, out):
+        d = self._new(OP_SOFTMAX_ROWS).u.aux
+        d.x, d.ld_x, d.out, d.ld_out, d.n, d.C = _p(x), x.stride(0), _p(out), out.stride(0), x.shape[0], x.shape[1]
+        self.hold(x, out)
+
+    def postprocess_u8(self, img_nchw, out_u8):
+        d = self._new(OP_POSTPROCESS_U8).u.aux
+        B, C, H, W = img_nchw.shape
+        d.x, d.out, d.n, d.B, d.C = _p(img_nchw), _p(out_u8), H * W, B, C
+        self.hold(img_nchw, out_u8)
 
     # -- lifecycle --------------------------------------------------------------------------
     def finalize(self):

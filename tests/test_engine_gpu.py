@@ -16,6 +16,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+VAE_TEST_CHANNELS = (64, 64, 128, 128)     # the native decoder needs channel counts that are multiples of 64
 
 
 def _cases():
@@ -72,7 +73,8 @@ def _pair(turbo, seed=0):
     from oracle.vae import tiny_vae_config
     name = "synthetic/sdxl-turbo-tiny" if turbo else "synthetic/sdxl-base-tiny"
     ocfg = tiny_config()
-    op = OraclePipe(name, unet_cfg=ocfg, vae_cfg=tiny_vae_config(), seed=seed)
+    from oracle.vae import VAEConfig
+    op = OraclePipe(name, unet_cfg=ocfg, vae_cfg=VAEConfig(block_out_channels=VAE_TEST_CHANNELS), seed=seed)
     with torch.no_grad():
         for m in (op.unet, op.vae):
             for p in m.parameters():
@@ -80,7 +82,7 @@ def _pair(turbo, seed=0):
     lp = LPIPSAlex(seed=2)
     cfg = UNetConfig(**{f.name: getattr(ocfg, f.name) for f in dataclasses.fields(ocfg)})
     pp = SyntheticSDXLPipe(name, "cuda:0", unet_cfg=cfg, unet_state_dict=op.unet.state_dict(),
-                           vae_state_dict=op.vae.state_dict(), vae_channels=tiny_vae_config().block_out_channels,
+                           vae_state_dict=op.vae.state_dict(), vae_channels=VAE_TEST_CHANNELS,
                            lpips_state_dict={k: v for k, v in lp.state_dict().items() if "s." in k})
     return op, pp, lp
 

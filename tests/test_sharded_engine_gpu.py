@@ -23,7 +23,7 @@ def _build(dev):
     from latentblending_b200.unet import UNetConfig
     cfg = UNetConfig(block_out_channels=(64, 128, 256), transformer_layers=(0, 1, 2), cross_attention_dim=128,
                      addition_time_embed_dim=32, pooled_dim=64, sample_size=16)
-    pipe = SyntheticSDXLPipe("synthetic/sdxl-base-tiny", dev, unet_cfg=cfg, seed=5, vae_channels=(32, 32, 64, 64))
+    pipe = SyntheticSDXLPipe("synthetic/sdxl-base-tiny", dev, unet_cfg=cfg, seed=5, vae_channels=(64, 64, 128, 128))
     be = BlendingEngine(pipe, run_benchmark=False)
     be.set_dimensions((128, 128))
     be.set_num_inference_steps(10)
