@@ -1,5 +1,6 @@
 // api.cu -- context and error plumbing of the C ABI (include/lb200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -12,6 +13,12 @@ void lb_set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool lb_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) v = getenv("LB_NO_PDL") ? 0 : 1;
+    return v != 0;
 }
 
 extern "C" int lb_abi_version(void) { return LB_ABI_VERSION; }

@@ -44,6 +44,7 @@ constexpr uint32_t kTmemCols = 512;             // S0 [0,128) S1 [128,256) O0 [2
 //   softmax WG1:       -------- softmax(S1[j]) ------ | ...
 // Each half's softmax overlaps the other half's MMAs; K/V tiles are loaded once per 256 query rows.
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         // ---------------- TMA producer (warp-uniform loop, one elected lane issues) ----------------
@@ -361,7 +363,7 @@ int attn_plan_launch(const AttnPlan& plan, cudaStream_t st) {
         LB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         attr_set = true;
     }
-    attn_tc_kernel<<<plan.grid, kAttnThreads, kAttnSmem, st>>>(plan.p);
+    lb_launch_pdl(attn_tc_kernel, plan.grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, plan.p);
     LB_LAUNCH_CHECK();
     return 0;
 }

@@ -52,6 +52,33 @@ static inline cudaStream_t lb_stream(void* s) { return reinterpret_cast<cudaStre
 static inline bool lb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int64_t lb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- launches: programmatic dependent launch (PDL) ---------------------------------------------
+// Every kernel of the library is launched with programmatic stream serialization and starts with
+// griddepcontrol.launch_dependents / griddepcontrol.wait: the NEXT kernel's launch latency, block scheduling and
+// prologue (barrier init, TMEM allocation, descriptor prefetch) overlap this kernel's execution; its
+// griddepcontrol.wait returns only when this grid has completed and its writes are visible.
+#ifdef __CUDACC__
+#include <utility>
+bool lb_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = lb_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // ---- device helpers ---------------------------------------------------------
 #ifdef __CUDACC__
 // fp16 rounding of an fp32 value exactly as a torch fp16 op stores it

@@ -63,6 +63,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 template <int BN, int CL>
 __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     using C = Cfg<BN>;
+    pdl_launch_dependents();       // the next kernel may start its launch + prologue while this one runs
     const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
     if (CL == 2) cluster_sync_all();          // peer barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                               // everything above overlapped the previous kernel; its outputs are visible now
 
     // tile index space: (m-group, n) with CL vertically adjacent M tiles per group
     const int m_groups = (p.tiles_m + CL - 1) / CL;
@@ -368,13 +370,15 @@ template <int BN, int CL> int launch_bn_cl(const GemmPlan& plan, cudaStream_t st
     cfg.blockDim = dim3(kThreadsGemm);
     cfg.dynamicSmemBytes = Cfg<BN>::smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = lb_pdl_enabled() ? 2 : 1;
     LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, plan.p));
     return 0;
 }

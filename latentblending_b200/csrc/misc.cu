@@ -21,6 +21,8 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x));
 __global__ void embed_inputs_kernel(float t, const __half* __restrict__ text_embeds, const __half* __restrict__ time_ids,
                                     int B, int dim_t, int pooled, int dim_a, __half* __restrict__ temb_in,
                                     __half* __restrict__ add_in) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x;
     const int half_t = dim_t / 2, half_a = dim_a / 2;
     const int add_w = pooled + 6 * dim_a;
@@ -52,6 +54,8 @@ __global__ void __launch_bounds__(kThreads)
 linear_small_kernel(const __half* __restrict__ x, long long ldx, int M, int K, const __half* __restrict__ w,
                     long long ldw, const __half* __restrict__ bias, const __half* __restrict__ addend,
                     long long ldadd, int act_in, int act_out, __half* __restrict__ out, long long ldo, int N) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * (kThreads / 32) + warp;
     if (n >= N) return;
@@ -105,6 +109,8 @@ linear_small_kernel(const __half* __restrict__ x, long long ldx, int M, int K, c
 __global__ void __launch_bounds__(kThreads)
 conv_in_kernel(const __half* __restrict__ x, int B, int Cin, int H, int W, const __half* __restrict__ wp,
                const __half* __restrict__ bias, int Cout, __half* __restrict__ out, long long ldo) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __half s_w[];   // [9*Cin][Cout]
     const int wn = 9 * Cin * Cout;
     for (int i = threadIdx.x; i < wn; i += kThreads) s_w[i] = wp[i];
@@ -160,6 +166,8 @@ conv_in_kernel(const __half* __restrict__ x, int B, int Cin, int H, int W, const
 __global__ void __launch_bounds__(kThreads)
 conv_out_kernel(const __half* __restrict__ x, long long ld, int B, int Cin, int H, int W,
                 const __half* __restrict__ wp, const __half* __restrict__ bias, int Cout, __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __half s_w[];   // [Cout][9][Cin]
     const int wn = Cout * 9 * Cin;
     for (int i = threadIdx.x; i < wn; i += kThreads) s_w[i] = wp[i];
@@ -207,6 +215,8 @@ conv_out_kernel(const __half* __restrict__ x, long long ld, int B, int Cin, int 
 __global__ void __launch_bounds__(kThreads)
 upsample2x_kernel(const __half* __restrict__ x, long long ld, int B, int H, int W, int C, __half* __restrict__ out,
                   long long ldo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int vecs = C >> 3;
     const long long total = (long long)B * 2 * H * 2 * W * vecs;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
@@ -221,6 +231,8 @@ upsample2x_kernel(const __half* __restrict__ x, long long ld, int B, int H, int 
 // ---- im2col for the 3x3 stride-2 pad-1 downsample convs: out[B*Ho*Wo, 9*C], K order (ky,kx,c) ------
 __global__ void __launch_bounds__(kThreads)
 im2col_s2_kernel(const __half* __restrict__ x, long long ld, int B, int H, int W, int C, __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;   // floor((H + 2 - 3)/2) + 1
     const int vecs = C >> 3;
     const long long total = (long long)B * Ho * Wo * 9 * vecs;
@@ -251,7 +263,7 @@ extern "C" int lb_embed_inputs(lb_ctx* ctx, float t, const void* text_embeds, co
                                int dim_t, int pooled, int dim_a, void* temb_in, void* add_in, void* stream) {
     LB_REQUIRE(ctx && text_embeds && time_ids && temb_in && add_in, "lb_embed_inputs: null argument");
     LB_REQUIRE(dim_t % 2 == 0 && dim_a % 2 == 0 && B >= 1, "lb_embed_inputs: bad sizes");
-    embed_inputs_kernel<<<B, kThreads, 0, lb_stream(stream)>>>(t, (const __half*)text_embeds, (const __half*)time_ids, B,
+    lb_launch_pdl(embed_inputs_kernel, B, kThreads, 0, lb_stream(stream), t, (const __half*)text_embeds, (const __half*)time_ids, B,
                                                               dim_t, pooled, dim_a, (__half*)temb_in, (__half*)add_in);
     LB_LAUNCH_CHECK();
     return 0;
@@ -267,7 +279,7 @@ extern "C" int lb_linear_small(lb_ctx* ctx, const void* x, int64_t ldx, int M, i
     const unsigned grid = (unsigned)lb_ceil_div(N, kThreads / 32);
     cudaStream_t st = lb_stream(stream);
 #define LB_LS(MM)                                                                                                    \
-    linear_small_kernel<MM><<<grid, kThreads, 0, st>>>((const __half*)x, ldx, M, K, (const __half*)w, ldw,            \
+    lb_launch_pdl(linear_small_kernel<MM>, grid, kThreads, 0, st, (const __half*)x, ldx, M, K, (const __half*)w, ldw,            \
                                                        (const __half*)bias, (const __half*)addend, ldadd, act_in,     \
                                                        act_out, (__half*)out, ldo, N)
     if (M <= 2) LB_LS(2);
@@ -293,7 +305,7 @@ extern "C" int lb_conv_in(lb_ctx* ctx, const void* x_nchw, int B, int Cin, int H
     const long long npix = (long long)B * H * W;
     unsigned grid = (unsigned)lb_ceil_div(npix, kThreads / 32);
     if (grid > (unsigned)ctx->sm_count * 4) grid = ctx->sm_count * 4;
-    conv_in_kernel<<<grid, kThreads, smem, lb_stream(stream)>>>((const __half*)x_nchw, B, Cin, H, W,
+    lb_launch_pdl(conv_in_kernel, grid, kThreads, smem, lb_stream(stream), (const __half*)x_nchw, B, Cin, H, W,
                                                                (const __half*)w_packed, (const __half*)bias, Cout,
                                                                (__half*)out, ldo);
     LB_LAUNCH_CHECK();
@@ -314,7 +326,7 @@ extern "C" int lb_conv_out(lb_ctx* ctx, const void* x, int64_t ld, int B, int Ci
     const long long npix = (long long)B * H * W;
     unsigned grid = (unsigned)lb_ceil_div(npix, kThreads / 32);
     if (grid > (unsigned)ctx->sm_count * 8) grid = ctx->sm_count * 8;
-    conv_out_kernel<<<grid, kThreads, smem, lb_stream(stream)>>>((const __half*)x, ld, B, Cin, H, W,
+    lb_launch_pdl(conv_out_kernel, grid, kThreads, smem, lb_stream(stream), (const __half*)x, ld, B, Cin, H, W,
                                                                 (const __half*)w_packed, (const __half*)bias, Cout,
                                                                 (__half*)out_nchw);
     LB_LAUNCH_CHECK();
@@ -326,7 +338,7 @@ extern "C" int lb_upsample2x(lb_ctx* ctx, const void* x, int64_t ld, int B, int 
     LB_REQUIRE(ctx && x && out, "lb_upsample2x: null argument");
     LB_REQUIRE(C % 8 == 0 && ld % 8 == 0 && ldo % 8 == 0, "lb_upsample2x: C and strides must be multiples of 8");
     const long long total = (long long)B * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<grid_for(total, ctx->sm_count), kThreads, 0, lb_stream(stream)>>>((const __half*)x, ld, B, H, W, C,
+    lb_launch_pdl(upsample2x_kernel, grid_for(total, ctx->sm_count), kThreads, 0, lb_stream(stream), (const __half*)x, ld, B, H, W, C,
                                                                                          (__half*)out, ldo);
     LB_LAUNCH_CHECK();
     return 0;
@@ -336,7 +348,7 @@ extern "C" int lb_im2col_s2(lb_ctx* ctx, const void* x, int64_t ld, int B, int H
     LB_REQUIRE(ctx && x && out, "lb_im2col_s2: null argument");
     LB_REQUIRE(C % 8 == 0 && ld % 8 == 0, "lb_im2col_s2: C and stride must be multiples of 8");
     const long long total = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * 9 * (C / 8);
-    im2col_s2_kernel<<<grid_for(total, ctx->sm_count), kThreads, 0, lb_stream(stream)>>>((const __half*)x, ld, B, H, W, C,
+    lb_launch_pdl(im2col_s2_kernel, grid_for(total, ctx->sm_count), kThreads, 0, lb_stream(stream), (const __half*)x, ld, B, H, W, C,
                                                                                         (__half*)out);
     LB_LAUNCH_CHECK();
     return 0;
@@ -349,6 +361,8 @@ namespace {
 __global__ void __launch_bounds__(kThreads)
 latent_prep_kernel(const __half* __restrict__ x, int B, int C, long long hw, const float* __restrict__ w /*[C][C]*/,
                    const float* __restrict__ bias, __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = (long long)B * hw;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
         const long long b = i / hw, p = i % hw;
@@ -365,6 +379,8 @@ latent_prep_kernel(const __half* __restrict__ x, int B, int C, long long hw, con
 // row softmax (in place capable): out[r,:] = softmax(x[r,:]) over `cols` fp16 values, one CTA per row.
 __global__ void __launch_bounds__(kThreads)
 softmax_rows_kernel(const __half* __restrict__ x, long long ld, int cols, __half* __restrict__ out, long long ldo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long r = blockIdx.x;
     const __half* xr = x + r * ld;
     __half* orow = out + r * ldo;
@@ -430,6 +446,8 @@ softmax_rows_kernel(const __half* __restrict__ x, long long ld, int cols, __half
 // VaeImageProcessor.postprocess: NCHW fp16 image -> uint8 NHWC, (x/2+0.5).clamp(0,1)*255 rounded half-to-even
 __global__ void __launch_bounds__(kThreads)
 postprocess_u8_kernel(const __half* __restrict__ img, int B, int C, long long hw, uint8_t* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = (long long)B * hw * C;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
         const int c = (int)(i % C);
@@ -445,7 +463,7 @@ extern "C" int lb_latent_prep(lb_ctx* ctx, const void* x_nchw, int B, int C, int
                               const void* bias_f32, void* out_nchw, void* stream) {
     LB_REQUIRE(ctx && x_nchw && w_f32 && bias_f32 && out_nchw, "lb_latent_prep: null argument");
     LB_REQUIRE(C >= 1 && C <= 8, "lb_latent_prep: C must be <= 8");
-    latent_prep_kernel<<<grid_for((long long)B * hw, ctx->sm_count), kThreads, 0, lb_stream(stream)>>>(
+    lb_launch_pdl(latent_prep_kernel, grid_for((long long)B * hw, ctx->sm_count), kThreads, 0, lb_stream(stream), 
         (const __half*)x_nchw, B, C, hw, (const float*)w_f32, (const float*)bias_f32, (__half*)out_nchw);
     LB_LAUNCH_CHECK();
     return 0;
@@ -458,7 +476,7 @@ extern "C" int lb_softmax_rows(lb_ctx* ctx, const void* x, int64_t ld, int64_t r
                "lb_softmax_rows: cols / strides must be multiples of 8, bases 16B aligned");
     LB_REQUIRE(rows <= 2147483647LL, "lb_softmax_rows: too many rows");
     if (rows == 0) return 0;
-    softmax_rows_kernel<<<(unsigned)rows, kThreads, 0, lb_stream(stream)>>>((const __half*)x, ld, cols, (__half*)out, ldo);
+    lb_launch_pdl(softmax_rows_kernel, (unsigned)rows, kThreads, 0, lb_stream(stream), (const __half*)x, ld, cols, (__half*)out, ldo);
     LB_LAUNCH_CHECK();
     return 0;
 }
@@ -466,7 +484,7 @@ extern "C" int lb_softmax_rows(lb_ctx* ctx, const void* x, int64_t ld, int64_t r
 extern "C" int lb_postprocess_u8(lb_ctx* ctx, const void* img_nchw, int B, int C, int64_t hw, void* out_u8_nhwc,
                                  void* stream) {
     LB_REQUIRE(ctx && img_nchw && out_u8_nhwc, "lb_postprocess_u8: null argument");
-    postprocess_u8_kernel<<<grid_for((long long)B * hw * C, ctx->sm_count), kThreads, 0, lb_stream(stream)>>>(
+    lb_launch_pdl(postprocess_u8_kernel, grid_for((long long)B * hw * C, ctx->sm_count), kThreads, 0, lb_stream(stream), 
         (const __half*)img_nchw, B, C, hw, (uint8_t*)out_u8_nhwc);
     LB_LAUNCH_CHECK();
     return 0;

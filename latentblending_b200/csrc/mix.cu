@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(kThreads)
 slerp_cluster_kernel(const T* __restrict__ p0, const T* __restrict__ p1, T* __restrict__ out, int64_t n,
                      int64_t stride0, int64_t stride1, int64_t stride_out, double fract,
                      const double* __restrict__ fract_rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int VE = Vec<T>::N;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned crank = cluster.block_rank();
@@ -183,6 +185,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 slerp_partial_kernel(const T* __restrict__ p0, const T* __restrict__ p1, int64_t n, int64_t stride0,
                      int64_t stride1, double* __restrict__ partials) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t row = blockIdx.y;
     const T* a_row = p0 + row * stride0;
     const T* b_row = p1 + row * stride1;
@@ -208,6 +212,8 @@ __global__ void __launch_bounds__(kThreads)
 slerp_apply_kernel(const T* __restrict__ p0, const T* __restrict__ p1, T* __restrict__ out, int64_t n,
                    int64_t stride0, int64_t stride1, int64_t stride_out, double fract,
                    const double* __restrict__ fract_rows, const double* __restrict__ partials) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t row = blockIdx.y;
     double aa = 0.0, bb = 0.0, ab = 0.0;
     for (int p = 0; p < kParts; ++p) {
@@ -229,6 +235,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 lerp_kernel(const T* __restrict__ p0, const T* __restrict__ p1, T* __restrict__ out, int64_t n, float w0,
             float w1) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
         // torch: (1-f)*p0 -> store dtype; f*p1 -> store dtype; add -> store dtype
         T a, b;
@@ -283,12 +291,12 @@ int slerp_dispatch(const void* p0v, const void* p1v, void* outv, int64_t rows, i
     LB_REQUIRE(ws != nullptr, "lb_slerp_rows: generic path needs the workspace");
     LB_REQUIRE(rows <= 65535, "lb_slerp_rows: rows > 65535 unsupported");
     double* partials = static_cast<double*>(ws);
-    slerp_partial_kernel<T><<<dim3(kParts, (unsigned)rows), kThreads, 0, st>>>(p0, p1, n, s0, s1, partials);
+    lb_launch_pdl(slerp_partial_kernel<T>, dim3(kParts, (unsigned)rows), kThreads, 0, st, p0, p1, n, s0, s1, partials);
     LB_LAUNCH_CHECK();
     unsigned gx = (unsigned)lb_ceil_div(n, (int64_t)kThreads * 8);
     if (gx < 1) gx = 1;
     if (gx > 1024) gx = 1024;
-    slerp_apply_kernel<T><<<dim3(gx, (unsigned)rows), kThreads, 0, st>>>(p0, p1, out, n, s0, s1, so, fract,
+    lb_launch_pdl(slerp_apply_kernel<T>, dim3(gx, (unsigned)rows), kThreads, 0, st, p0, p1, out, n, s0, s1, so, fract,
                                                                          fract_rows, partials);
     LB_LAUNCH_CHECK();
     return 0;
@@ -328,9 +336,9 @@ extern "C" int lb_lerp(lb_ctx* ctx, const void* p0, const void* p1, void* out, i
     if (grid < 1) grid = 1;
     cudaStream_t st = lb_stream(stream);
     if (dtype == 0)
-        lerp_kernel<__half><<<grid, kThreads, 0, st>>>((const __half*)p0, (const __half*)p1, (__half*)out, n, w0, w1);
+        lb_launch_pdl(lerp_kernel<__half>, grid, kThreads, 0, st, (const __half*)p0, (const __half*)p1, (__half*)out, n, w0, w1);
     else
-        lerp_kernel<float><<<grid, kThreads, 0, st>>>((const float*)p0, (const float*)p1, (float*)out, n, w0, w1);
+        lb_launch_pdl(lerp_kernel<float>, grid, kThreads, 0, st, (const float*)p0, (const float*)p1, (float*)out, n, w0, w1);
     LB_LAUNCH_CHECK();
     return 0;
 }

@@ -21,6 +21,8 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 __global__ void __launch_bounds__(kThreads)
 gn_partial_kernel(const __half* __restrict__ x, long long ld, int C, int HW, int groups, int rows_per_chunk,
                   float2* __restrict__ partial /*[B][chunks][groups]*/) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
     const int row0 = chunk * rows_per_chunk;
     const int row1 = min(HW, row0 + rows_per_chunk);
@@ -57,6 +59,8 @@ gn_apply_kernel(const __half* __restrict__ x, long long ld, int C, int HW, int g
                 const float2* __restrict__ partial, const __half* __restrict__ gamma,
                 const __half* __restrict__ beta, float eps, int do_silu, __half* __restrict__ out, long long ldo,
                 int rows_per_block) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y;
     __shared__ float s_mean[64], s_rstd[64];
     __shared__ float s_scale[kMaxC], s_shift[kMaxC];
@@ -115,6 +119,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(kThreads)
 ln_kernel(const __half* __restrict__ x, long long ld, long long rows, int C, const __half* __restrict__ gamma,
           const __half* __restrict__ beta, float eps, __half* __restrict__ out, long long ldo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (kThreads / 32) + warp;
     if (row >= rows) return;
@@ -202,7 +208,7 @@ extern "C" int lb_groupnorm(lb_ctx* ctx, const void* x, int64_t ld, int B, int H
     const int rpc = (int)lb_ceil_div(HW, chunks);
     const int used_chunks = (int)lb_ceil_div(HW, rpc);
     cudaStream_t st = lb_stream(stream);
-    gn_partial_kernel<<<dim3(used_chunks, B), kThreads, 0, st>>>((const __half*)x, ld, C, HW, groups, rpc,
+    lb_launch_pdl(gn_partial_kernel, dim3(used_chunks, B), kThreads, 0, st, (const __half*)x, ld, C, HW, groups, rpc,
                                                                 (float2*)workspace);
     LB_LAUNCH_CHECK();
     // apply: ~4 blocks per SM
@@ -210,7 +216,7 @@ extern "C" int lb_groupnorm(lb_ctx* ctx, const void* x, int64_t ld, int B, int H
     if (blocks > HW) blocks = HW;
     const int rpb = (int)lb_ceil_div(HW, blocks);
     blocks = (int)lb_ceil_div(HW, rpb);
-    gn_apply_kernel<<<dim3(blocks, B), kThreads, 0, st>>>((const __half*)x, ld, C, HW, groups, used_chunks,
+    lb_launch_pdl(gn_apply_kernel, dim3(blocks, B), kThreads, 0, st, (const __half*)x, ld, C, HW, groups, used_chunks,
                                                           (const float2*)workspace, (const __half*)gamma,
                                                           (const __half*)beta, eps, silu, (__half*)out, ldo, rpb);
     LB_LAUNCH_CHECK();
@@ -228,13 +234,13 @@ extern "C" int lb_layernorm(lb_ctx* ctx, const void* x, int64_t ld, int64_t rows
     cudaStream_t st = lb_stream(stream);
     const int vecs = C / 8;
     if (vecs <= 64)
-        ln_kernel<2><<<grid, kThreads, 0, st>>>((const __half*)x, ld, rows, C, (const __half*)gamma,
+        lb_launch_pdl(ln_kernel<2>, grid, kThreads, 0, st, (const __half*)x, ld, rows, C, (const __half*)gamma,
                                                 (const __half*)beta, eps, (__half*)out, ldo);
     else if (vecs <= 160)
-        ln_kernel<5><<<grid, kThreads, 0, st>>>((const __half*)x, ld, rows, C, (const __half*)gamma,
+        lb_launch_pdl(ln_kernel<5>, grid, kThreads, 0, st, (const __half*)x, ld, rows, C, (const __half*)gamma,
                                                 (const __half*)beta, eps, (__half*)out, ldo);
     else
-        ln_kernel<8><<<grid, kThreads, 0, st>>>((const __half*)x, ld, rows, C, (const __half*)gamma,
+        lb_launch_pdl(ln_kernel<8>, grid, kThreads, 0, st, (const __half*)x, ld, rows, C, (const __half*)gamma,
                                                 (const __half*)beta, eps, (__half*)out, ldo);
     LB_LAUNCH_CHECK();
     return 0;

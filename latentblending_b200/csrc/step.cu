@@ -20,6 +20,8 @@ __device__ __forceinline__ float h(float x) { return lb_round_h(x); }
 
 __global__ void __launch_bounds__(kThreads)
 scale_input_kernel(const __half* __restrict__ x, __half* __restrict__ out, int64_t n, int batch, float divisor) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
         __half v = __float2half_rn(__fdiv_rn(__half2float(x[i]), divisor));
         for (int b = 0; b < batch; ++b) out[(int64_t)b * n + i] = v;
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(kThreads)
 cfg_euler_kernel(const __half* __restrict__ x, const __half* __restrict__ eps, const __half* __restrict__ noise,
                  __half* __restrict__ out, __half* __restrict__ traj, int64_t n, int use_cfg, float g,
                  float sigma, float dt, float sigma_up) {
+    pdl_launch_dependents();
+    pdl_wait();
     const bool has_noise = noise != nullptr;
     const bool vec = (n % 8 == 0);
     if (vec) {
@@ -94,7 +98,7 @@ extern "C" int lb_scale_model_input(lb_ctx* ctx, const void* latents, void* out,
     LB_REQUIRE(batch >= 1 && n > 0, "lb_scale_model_input: bad sizes");
     unsigned grid = (unsigned)lb_ceil_div(n, kThreads);
     if (grid > 148 * 8) grid = 148 * 8;
-    scale_input_kernel<<<grid, kThreads, 0, lb_stream(stream)>>>((const __half*)latents, (__half*)out, n, batch,
+    lb_launch_pdl(scale_input_kernel, grid, kThreads, 0, lb_stream(stream), (const __half*)latents, (__half*)out, n, batch,
                                                                 divisor);
     LB_LAUNCH_CHECK();
     return 0;
@@ -113,7 +117,7 @@ extern "C" int lb_cfg_euler_step(lb_ctx* ctx, const void* latents, const void* e
     unsigned grid = (unsigned)lb_ceil_div(n, (int64_t)kThreads * 8);
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
-    cfg_euler_kernel<<<grid, kThreads, 0, lb_stream(stream)>>>((const __half*)latents, (const __half*)eps,
+    lb_launch_pdl(cfg_euler_kernel, grid, kThreads, 0, lb_stream(stream), (const __half*)latents, (const __half*)eps,
                                                               (const __half*)noise, (__half*)out, (__half*)traj, n,
                                                               use_cfg, guidance, sigma, dt, sigma_up);
     LB_LAUNCH_CHECK();
