@@ -9,7 +9,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from latentblending_b200 import ops  # noqa: E402
 
 
-def time_it(fn, iters=20, warm=5):
+ITERS = int(os.environ.get('BENCH_ITERS', 20))
+WARM = int(os.environ.get('BENCH_WARM', 5))
+
+
+def time_it(fn, iters=None, warm=None):
+    iters = ITERS if iters is None else iters
+    warm = WARM if warm is None else warm
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()

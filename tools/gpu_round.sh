@@ -1,0 +1,35 @@
+#!/bin/bash
+# One gpurun call: GPU tests, micro-benchmarks, bench line, ncu launch list and ncu full captures.
+# usage (under gpurun): bash tools/gpu_round.sh <tag> [sections...]   sections: tests ops bench launches ncu
+set -u
+TAG=${1:-rXX}; shift || true
+SECTIONS=${*:-tests ops bench launches ncu}
+O=gpurun_out/$TAG; mkdir -p $O
+python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1 || { echo BUILD FAILED; tail -20 $O/build.log; exit 1; }
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/nvsmi.txt
+for s in $SECTIONS; do
+case $s in
+tests)
+  ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $O/pytest.log 2>&1; echo "pytest exit $?"; tail -5 $O/pytest.log ;;
+smoke)
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke exit $?"; tail -3 $O/smoke.log ;;
+ops)
+  timeout 300 python tools/bench_ops.py attn gemm > $O/bench_ops.txt 2>&1; cat $O/bench_ops.txt
+  timeout 300 python tools/bench_mix.py > $O/bench_mix.txt 2>&1; cat $O/bench_mix.txt ;;
+bench)
+  timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench.json 2> $O/bench.err; echo "bench exit $?"; cat $O/bench.json; tail -3 $O/bench.err ;;
+parts)
+  timeout 600 python tools/time_parts.py > $O/time_parts.txt 2>&1; head -12 $O/time_parts.txt ;;
+launches)
+  timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+     --log-file $O/unet_launches.csv python tools/profile_unet.py > $O/unet_launches.log 2>&1; echo "launches exit $?" ;;
+ncu)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_tc -c 5 -o $O/attn -f \
+     env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_ops.py attn > $O/ncu_attn.log 2>&1; echo "ncu attn exit $?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 12 -o $O/gemm -f \
+     env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_ops.py gemm > $O/ncu_gemm.log 2>&1; echo "ncu gemm exit $?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:slerp_cluster -s 105 -c 1 -o $O/mix -f \
+     python tools/bench_mix.py > $O/ncu_mix.log 2>&1; echo "ncu mix exit $?" ;;
+esac
+done
+ls -la $O
