@@ -5,179 +5,41 @@
 // crossfeed diffusers_holder.py:322-324.  HBM-bound: 2 reads + 1 write per
 // element (6 B/elem in fp16).
 //
-// Fast path (slerp_cluster_kernel): one thread-block CLUSTER per row.  Each CTA
-// keeps its slice of both inputs in registers, the three fp64 row reductions
-// (|p0|^2, |p1|^2, <p0,p1>) are combined across the cluster through distributed
-// shared memory, and the axpby is applied to the registers -- a single pass
-// over HBM with 128-bit streaming loads/stores.
+// Fast path (slerp_l2_kernel, mix_kernels.cuh): one thread-block CLUSTER per row.
+// Pass 1 streams each CTA's slice of both inputs from HBM (L2 evict_last hint) into
+// the three fp64 row reductions (|p0|^2, |p1|^2, <p0,p1>), combined across the cluster
+// through distributed shared memory; the acos/sin weights are computed once per row and
+// broadcast over DSMEM; pass 2 re-reads the slice from L2 (evict_first), evaluates the
+// axpby with a certified fp32 fast path (exact fp64 fallback per element pair) and writes
+// 128-bit streaming stores -- DRAM sees 2 reads + 1 write per element.
 // Generic path (any n / alignment): partial-sum kernel + apply kernel through a
 // small workspace; deterministic (fixed summation order, no atomics).
-#include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "mix_kernels.cuh"
 
-namespace cg = cooperative_groups;
+using namespace lbmix;
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kParts = 8;  // partials per row in the generic path
-constexpr double kClampEps = 1e-7;  // utils.py:55
 
-template <typename T> struct Vec;
-template <> struct Vec<__half> {
-    static constexpr int N = 8;
-    __device__ static void unpack(const uint4& v, float (&f)[8]) {
-        const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float2 t = __half22float2(h[i]);
-            f[2 * i] = t.x;
-            f[2 * i + 1] = t.y;
-        }
-    }
-    __device__ static uint4 pack(const float (&f)[8]) {
-        uint4 v;
-        __half2* h = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-        return v;
-    }
-};
-template <> struct Vec<float> {
-    static constexpr int N = 4;
-    __device__ static void unpack(const uint4& v, float (&f)[4]) {
-        f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
-        f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
-    }
-    __device__ static uint4 pack(const float (&f)[4]) {
-        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
-                          __float_as_uint(f[3]));
-    }
-};
+// LB_SLERP_EXACT=1: evaluate pass 2 in fp64 for every element (the reference arithmetic verbatim) instead of the
+// certified fp32 path -- same bits, used by the tests to A/B the certification.
+bool lb_slerp_exact_pass2() {
+    const char* e = getenv("LB_SLERP_EXACT");
+    return e && e[0] == '1';
+}
 
 __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ void from_f(__half* p, float v) { *p = __float2half_rn(v); }
 __device__ __forceinline__ void from_f(float* p, float v) { *p = v; }
 
-// utils.py:54-63 in fp64: the two slerp weights from the three row sums.
-__device__ __forceinline__ void slerp_weights(double aa, double bb, double ab, double fract, double& s0,
-                                              double& s1) {
-    double norm = sqrt(aa) * sqrt(bb);
-    double dot = ab / norm;
-    dot = fmin(fmax(dot, -1.0 + kClampEps), 1.0 - kClampEps);
-    double theta0 = acos(dot);
-    double sin0 = sin(theta0);
-    double theta_t = theta0 * fract;
-    s0 = sin(theta0 - theta_t) / sin0;
-    s1 = sin(theta_t) / sin0;
-}
-
-// fp64 axpby without FMA contraction (torch: mul, mul, add), then the
-// reference's fp64 -> fp32 -> storage-dtype cast chain.
-__device__ __forceinline__ float slerp_elem(float a, float b, double s0, double s1) {
-    double r = __dadd_rn(__dmul_rn((double)a, s0), __dmul_rn((double)b, s1));
-    return __double2float_rn(r);
-}
-
-__device__ __forceinline__ void block_reduce3(double& aa, double& bb, double& ab, double* sm /*[3*8]*/) {
-    aa = lb_warp_sum(aa);
-    bb = lb_warp_sum(bb);
-    ab = lb_warp_sum(ab);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) {
-        sm[w] = aa;
-        sm[8 + w] = bb;
-        sm[16 + w] = ab;
-    }
-    __syncthreads();
-    aa = bb = ab = 0.0;
-#pragma unroll
-    for (int i = 0; i < kThreads / 32; ++i) {
-        aa += sm[i];
-        bb += sm[8 + i];
-        ab += sm[16 + i];
-    }
-}
-
-// ---- fast path: one cluster per row ----------------------------------------------
-template <typename T, int CHUNKS>
-__global__ void __launch_bounds__(kThreads)
-slerp_cluster_kernel(const T* __restrict__ p0, const T* __restrict__ p1, T* __restrict__ out, int64_t n,
-                     int64_t stride0, int64_t stride1, int64_t stride_out, double fract,
-                     const double* __restrict__ fract_rows) {
-    pdl_launch_dependents();
-    pdl_wait();
-    constexpr int VE = Vec<T>::N;
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned crank = cluster.block_rank();
-    const unsigned csize = cluster.num_blocks();
-    const int64_t row = blockIdx.y;
-    const T* a_row = p0 + row * stride0;
-    const T* b_row = p1 + row * stride1;
-    T* o_row = out + row * stride_out;
-
-    __shared__ double red[24];
-    __shared__ double cta_sum[3];
-
-    uint4 va[CHUNKS], vb[CHUNKS];
-    int64_t off[CHUNKS];
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-        int64_t v = ((int64_t)(crank * CHUNKS + c)) * kThreads + threadIdx.x;
-        off[c] = v * VE;
-        if (off[c] < n) {
-            va[c] = lb_ldg_stream(a_row + off[c]);
-            vb[c] = lb_ldg_stream(b_row + off[c]);
-        } else {
-            va[c] = make_uint4(0, 0, 0, 0);
-            vb[c] = make_uint4(0, 0, 0, 0);
-        }
-    }
-    double aa = 0.0, bb = 0.0, ab = 0.0;
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-        float fa[VE], fb[VE];
-        Vec<T>::unpack(va[c], fa);
-        Vec<T>::unpack(vb[c], fb);
-#pragma unroll
-        for (int e = 0; e < VE; ++e) {
-            double da = fa[e], db = fb[e];
-            aa = fma(da, da, aa);
-            bb = fma(db, db, bb);
-            ab = fma(da, db, ab);
-        }
-    }
-    block_reduce3(aa, bb, ab, red);
-    if (threadIdx.x == 0) {
-        cta_sum[0] = aa;
-        cta_sum[1] = bb;
-        cta_sum[2] = ab;
-    }
-    cluster.sync();
-    double taa = 0.0, tbb = 0.0, tab = 0.0;
-    for (unsigned r = 0; r < csize; ++r) {
-        const double* remote = cluster.map_shared_rank(cta_sum, r);
-        taa += remote[0];
-        tbb += remote[1];
-        tab += remote[2];
-    }
-    cluster.sync();  // nobody may exit while a peer still reads its cta_sum
-    const double f = fract_rows ? fract_rows[row] : fract;
-    double s0, s1;
-    slerp_weights(taa, tbb, tab, f, s0, s1);
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-        if (off[c] < n) {
-            float fa[VE], fb[VE], fo[VE];
-            Vec<T>::unpack(va[c], fa);
-            Vec<T>::unpack(vb[c], fb);
-#pragma unroll
-            for (int e = 0; e < VE; ++e) fo[e] = slerp_elem(fa[e], fb[e], s0, s1);
-            lb_stg_stream(o_row + off[c], Vec<T>::pack(fo));
-        }
-    }
+__device__ __forceinline__ void block_reduce3(double& aa, double& bb, double& ab, double* sm /*[96]*/) {
+    lbmix::block_reduce3<kThreads>(aa, bb, ab, sm);
 }
 
 // ---- generic path ---------------------------------------------------------------------
@@ -190,7 +52,7 @@ slerp_partial_kernel(const T* __restrict__ p0, const T* __restrict__ p1, int64_t
     const int64_t row = blockIdx.y;
     const T* a_row = p0 + row * stride0;
     const T* b_row = p1 + row * stride1;
-    __shared__ double red[24];
+    __shared__ double red[96];
     double aa = 0.0, bb = 0.0, ab = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)kParts * kThreads) {
         double da = to_f(a_row[i]), db = to_f(b_row[i]);
@@ -246,23 +108,32 @@ lerp_kernel(const T* __restrict__ p0, const T* __restrict__ p1, T* __restrict__ 
     }
 }
 
-template <typename T, int CHUNKS>
-int launch_cluster(const T* p0, const T* p1, T* out, int64_t rows, int64_t n, int64_t s0, int64_t s1,
-                   int64_t so, double fract, const double* fract_rows, int csize, cudaStream_t st) {
+// fast path launch: cluster of `csize` CTAs per row, `slice` elements of each input per CTA (two passes over
+// global memory, the second served by L2 -- see slerp_l2_kernel).  Tuned on B200 (tools/ubench_mix.cu,
+// profiles/r01c_mix_ubench.txt): 256 threads, 128 elements per thread and input, 4 CTAs resident per SM.
+constexpr int kFastThreads = 256;
+constexpr int kFastOcc = 1024;
+constexpr int64_t kSliceElemsTarget = 32768;
+
+template <typename T, bool EXACT2>
+int launch_fast(const T* p0, const T* p1, T* out, int64_t rows, int64_t n, int64_t s0, int64_t s1, int64_t so,
+                double fract, const double* fract_rows, int csize, int slice, cudaStream_t st) {
+    auto kern = slerp_l2_kernel<T, kFastThreads, EXACT2, true, kFastOcc>;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(csize, (unsigned)rows, 1);
-    cfg.blockDim = dim3(kThreads);
+    cfg.gridDim = dim3((unsigned)csize, (unsigned)rows, 1);
+    cfg.blockDim = dim3(kFastThreads);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.x = (unsigned)csize;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, slerp_cluster_kernel<T, CHUNKS>, p0, p1, out, n, s0, s1, so, fract,
-                                     fract_rows));
+    cfg.numAttrs = lb_pdl_enabled() ? 2 : 1;
+    LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p0, p1, out, n, slice, s0, s1, so, fract, fract_rows));
     return 0;
 }
 
@@ -275,18 +146,14 @@ int slerp_dispatch(const void* p0v, const void* p1v, void* outv, int64_t rows, i
     constexpr int VE = Vec<T>::N;
     const bool vec_ok = (n % VE == 0) && (s0 % VE == 0) && (s1 % VE == 0) && (so % VE == 0) &&
                         lb_aligned16(p0) && lb_aligned16(p1) && lb_aligned16(out);
-    const int64_t vecs = n / VE;
-    // cluster of up to 8 CTAs x 256 threads x CHUNKS vectors
-    if (vec_ok && vecs <= 8 * kThreads * 8 && rows <= 65535) {
-        const int64_t per_cta1 = kThreads;  // vectors per CTA at CHUNKS=1
+    if (vec_ok && rows <= 65535 && n <= (int64_t)1 << 30) {
+        // smallest power-of-two cluster (<= 8, the portable limit) whose slices are <= the target
         int csize = 1;
-        while (csize < 8 && (int64_t)csize * per_cta1 * 2 < vecs) csize *= 2;  // prefer >=2 chunks/thread before growing
-        while (csize < 8 && (int64_t)csize * per_cta1 * 8 < vecs) csize *= 2;
-        int64_t need = lb_ceil_div(vecs, (int64_t)csize * per_cta1);
-        if (need <= 1) return launch_cluster<T, 1>(p0, p1, out, rows, n, s0, s1, so, fract, fract_rows, csize, st);
-        if (need <= 2) return launch_cluster<T, 2>(p0, p1, out, rows, n, s0, s1, so, fract, fract_rows, csize, st);
-        if (need <= 4) return launch_cluster<T, 4>(p0, p1, out, rows, n, s0, s1, so, fract, fract_rows, csize, st);
-        return launch_cluster<T, 8>(p0, p1, out, rows, n, s0, s1, so, fract, fract_rows, csize, st);
+        while (csize < 8 && lb_ceil_div(n, csize) > kSliceElemsTarget) csize *= 2;
+        const int64_t slice = lb_ceil_div(lb_ceil_div(n, csize), VE) * VE;
+        if (sizeof(T) == 2 && !lb_slerp_exact_pass2())
+            return launch_fast<T, false>(p0, p1, out, rows, n, s0, s1, so, fract, fract_rows, csize, (int)slice, st);
+        return launch_fast<T, true>(p0, p1, out, rows, n, s0, s1, so, fract, fract_rows, csize, (int)slice, st);
     }
     LB_REQUIRE(ws != nullptr, "lb_slerp_rows: generic path needs the workspace");
     LB_REQUIRE(rows <= 65535, "lb_slerp_rows: rows > 65535 unsupported");

@@ -7,19 +7,19 @@
 //   s0 = sin(theta0 - theta0*f)/sin(theta0); s1 = sin(theta0*f)/sin(theta0);
 //   out = (storage dtype)(float)(p0*s0 + p1*s1)         [fp64 mul, mul, add, no FMA contraction]
 //
-// slerp_stage_kernel (fast path): one thread-block cluster per row.  Each CTA bulk-copies its slice of both
-// inputs into shared memory ONCE (cp.async.bulk, 16-128 KiB in flight per CTA with no register cost), so HBM
-// sees exactly 2 reads + 1 write per element (6 B/elem in fp16).
-//   pass 1 (smem): the three fp64 row sums; combined across the cluster through distributed shared memory in a
-//                  fixed order (deterministic, identical on every CTA).
-//   pass 2 (smem): the axpby.  The reference evaluates it in fp64 and rounds fp64 -> fp32 -> fp16; doing that per
-//                  element costs 3 fp64 conversions + 3 fp64 ops and makes the kernel fp64-pipe-bound, not
-//                  HBM-bound.  Instead each element is evaluated in fp32 with the weights split hi+lo
-//                  (|error| <= 2^-23 * (|a s0| + |b s1|), proven below) and the fp16 rounding is CERTIFIED: if the
-//                  fp32 value is farther from every fp16 rounding boundary than the error bound, rounding it gives
-//                  bit-for-bit the reference result; otherwise (~0.3 % of elements, subnormal / overflowing
-//                  results, NaN/Inf) that element takes the exact fp64 path.  Output is bit-identical to the
-//                  all-fp64 evaluation.
+// Two single-DRAM-pass designs live here (both bit-identical to the all-fp64 evaluation; A/B numbers in
+// profiles/r01c_mix_ubench.txt):
+//   slerp_l2_kernel    (the product path): pass 1 streams the row slice from HBM, pass 2 re-reads it from L2.
+//                      No on-chip staging -> ~48 registers, 4-6 CTAs per SM hide the serial section of each CTA
+//                      (row reduction -> cluster exchange -> acos/sin weights).  4.4 TB/s = 67 % of measured HBM.
+//   slerp_stage_kernel (kept as the measured alternative): cp.async.bulk stages the slice in shared memory once.
+//                      Exact 6 B/elem DRAM traffic, but only 3 CTAs fit per SM: 3.5 TB/s.
+// Pass 2 (the axpby): the reference evaluates it in fp64 and rounds fp64 -> fp32 -> fp16; doing that per element
+// costs 3 fp64 conversions + 3 fp64 ops and makes the kernel XU/fp64-pipe-bound (round-1a kernel: 2.1 TB/s).
+// Instead each element is evaluated in packed fp32 with the weights split hi+lo and the fp16 rounding is
+// CERTIFIED (derivation at slerp_vec8_h): if the fp32 value is farther from every fp16 rounding boundary than
+// the proven error bound, rounding it gives bit-for-bit the reference result; otherwise (~0.1 % of elements,
+// subnormal / overflowing results, NaN/Inf) that element pair takes the exact fp64 path.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
@@ -84,41 +84,145 @@ __device__ __forceinline__ float slerp_elem(float a, float b, double s0, double 
     return __double2float_rn(r);
 }
 
-// fp64 weight split into fp32 hi + lo (|s - hi - lo| <= 2^-48 |s|)
+// fp64 weight split into fp32 hi + lo (|s - hi - lo| <= 2^-48 |s|) plus the error-bound coefficients
 struct SplitW {
-    float s0h, s0l, s1h, s1l;
+    float s0h, s0l, s1h, s1l, e1;
+    __device__ SplitW() {}
     __device__ SplitW(double s0, double s1) {
         s0h = __double2float_rn(s0);
         s0l = __double2float_rn(s0 - (double)s0h);
         s1h = __double2float_rn(s1);
         s1l = __double2float_rn(s1 - (double)s1h);
+        e1 = fabsf(s1h) * kErrB;
     }
+    static constexpr float kErrR = 1.0625f * 1.1920928955078125e-07f;   // 1.0625 * 2^-23  (coefficient of |r|)
+    static constexpr float kErrB = 1.0625f * 5.9604644775390625e-08f;   // 1.0625 * 2^-24  (coefficient of |b s1h|)
 };
 
-// Certified fp16 result of (half)(float)(fp64(a)*s0 + fp64(b)*s1) for fp16-valued a, b.
-//   r = fma(a,s0h, fma(b,s1h, fma(a,s0l, b*s1l))):  with M = |a s0h| + |b s1h| the four roundings contribute
-//   2^-48 M, 2^-47 M, 2^-24 M(1+e), 2^-24 M(1+e)  =>  |r - x| <= 2^-23 M (1.01), x the exact real value; the
-//   reference's fp64 value R has |R - x| <= 2^-52 M.  E = 2^-22 M is used (2x margin, absorbs M's own rounding).
-//   Let u = half the fp16 spacing in r's binade and d = |r - RN16(r)|.  If d + E < u then R lies on the same
-//   side of the nearest rounding midpoint as r, and since |R - mid| > 2^-23 M >= ulp32(r)/2 so does RN32(R): the
-//   reference chain RN16(RN32(R)) equals RN16(r).  E < u/2 additionally covers R and r straddling a power of two
-//   (the finer grid below it).  Outside the normal fp16 range, or for NaN/Inf, the test fails -> exact path.
-__device__ __forceinline__ __half slerp_elem_h(float a, float b, const SplitW& w, double s0, double s1) {
+// ---- certified fp32 evaluation of (half)(float)(fp64(a)*s0 + fp64(b)*s1) for fp16-valued a, b -------------
+//   r  = fl(a s0h + t3), t3 = fl(b s1h + t2), t2 = fl(a s0l + t1), t1 = fl(b s1l)       (fp32, 4 operations)
+// Error vs the exact real x = a s0 + b s1, with M = |a s0| + |b s1|:
+//   |t1 - b s1l| <= 2^-48 |b s1|;  |t2 - (a s0l + t1)| <= 2^-24 |t2| <= 2^-48 M (1+e);
+//   |t3 - (b s1h + t2)| <= 2^-24 |t3| <= 2^-24 |b s1h| + 2^-48 M;   |r - (a s0h + t3)| <= 2^-24 |r|;
+//   the split itself loses <= 2^-48 M   =>   |r - x| <= B := 2^-24 (|r| + |b s1h|) + 2^-45 M,
+//   and M <= |r| + 2 |b s1h| (1+e) makes the last term < 2^-20 of the first.  The reference's fp64 value R
+//   (two products and a sum, each rounded) has |R - x| <= 2^-51 M.
+// Rounding: the reference returns RN16(RN32(R)).  Let mid be the fp16 rounding midpoint nearest to r, at distance
+//   m; u = half the fp16 spacing in r's binade; d = |r - RN16(r)| = u - m.  If m > B + ulp32(r)/2 then R is on
+//   r's side of mid AND farther than half an fp32 ulp from it, so RN32(R) is on that side too (never ON mid: no
+//   tie), hence RN16(RN32(R)) = RN16(r).  With ulp32(r)/2 <= 2^-24 |r| the test uses
+//       E = 1.0625 * 2^-24 * (2 |r| + |b s1h|)   >=  B + ulp32(r)/2   (6 % slack covers E's own two roundings)
+//       certified  <=>  E + max(d, E) < u         (d >= E: m = u - d > E;   d < E: 2E < u)
+//   2E < u also covers R and r straddling a power of two (finer grid below it): |R - 2^k| <= E < u/2 rounds to 2^k.
+//   No range test is needed: for |r| < 2^-14 (fp16 subnormals, coarser grid) u only gets stricter and turns negative
+//   below 2^-116; r >= 65520 rounds to inf so d = inf; NaN fails every comparison.  Uncertified elements (~0.1 %)
+//   are recomputed with the reference's fp64 arithmetic, so the output is bit-identical to the all-fp64 evaluation.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(reinterpret_cast<uint64_t&>(d))
+        : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)),
+          "l"(reinterpret_cast<const uint64_t&>(c)));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(reinterpret_cast<uint64_t&>(d))
+        : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+    return d;
+}
+// scalar form (used by the statistics kernel of tools/ubench_mix.cu; same arithmetic as the packed form)
+__device__ __forceinline__ float slerp_fast(float a, float b, const SplitW& w, float& E) {
     float t = b * w.s1l;
     t = fmaf(a, w.s0l, t);
     t = fmaf(b, w.s1h, t);
     const float r = fmaf(a, w.s0h, t);
-    const float M = fmaf(fabsf(a), fabsf(w.s0h), fabsf(b) * fabsf(w.s1h));
-    const float E = M * 2.384185791015625e-07f;   // 2^-22
-    const __half h = __float2half_rn(r);
-    const float d = fabsf(r - __half2float(h));
-    const uint32_t rb = __float_as_uint(r);
-    const float u = __uint_as_float((rb & 0x7f800000u) - (11u << 23));   // 2^(e-11); garbage if |r| < 2^-14 (rejected below)
-    const float ar = fabsf(r);
-    const bool ok = (E + fmaxf(d, E) < u) && (ar >= 6.103515625e-05f) && (ar < 65000.0f);
-    if (ok) return h;
-    return __float2half_rn(slerp_elem(a, b, s0, s1));
+    E = fmaf(fabsf(b), w.e1, fabsf(r) * SplitW::kErrR);
+    return r;
 }
+__device__ __forceinline__ bool slerp_certified_d(float r, float diff, float E) {   // diff = r - RN16(r)
+    const float u = __uint_as_float((__float_as_uint(r) & 0x7f800000u) - (11u << 23));   // 2^(e-11)
+    return E + fmaxf(fabsf(diff), E) < u;
+}
+__device__ __forceinline__ bool slerp_certified(float r, float back, float E) {
+    const float d = fabsf(r - back);
+    const float u = __uint_as_float((__float_as_uint(r) & 0x7f800000u) - (11u << 23));   // 2^(e-11)
+    return E + fmaxf(d, E) < u;
+}
+// exact path, kept out of line so the certified loop stays branch-over (not predicated fp64 code)
+__device__ __noinline__ uint32_t slerp_exact_bits(float a, float b, double s0, double s1) {
+    return (uint32_t)__half_as_ushort(__float2half_rn(slerp_elem(a, b, s0, s1)));
+}
+// 8 elements (one 128-bit vector of each input) -> 8 fp16 results; packed fp32 math, ONE branch per vector
+__device__ __forceinline__ uint4 slerp_vec8_h(const uint4& ua, const uint4& ub, const SplitW& w, double s0,
+                                              double s1) {
+    const __half2* ha = reinterpret_cast<const __half2*>(&ua);
+    const __half2* hb = reinterpret_cast<const __half2*>(&ub);
+    const float2 s0h = make_float2(w.s0h, w.s0h), s0l = make_float2(w.s0l, w.s0l);
+    const float2 s1h = make_float2(w.s1h, w.s1h), s1l = make_float2(w.s1l, w.s1l);
+    const float2 kr2 = make_float2(SplitW::kErrR, SplitW::kErrR), neg1 = make_float2(-1.f, -1.f);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+    bool okp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = __half22float2(ha[i]);
+        const float2 b = __half22float2(hb[i]);
+        float2 t = mul2(b, s1l);
+        t = fma2(a, s0l, t);
+        t = fma2(b, s1h, t);
+        const float2 r = fma2(a, s0h, t);
+        const __half2 h = __floats2half2_rn(r.x, r.y);
+        const float2 back = __half22float2(h);
+        ow[i] = *reinterpret_cast<const uint32_t*>(&h);
+        const float2 rk = mul2(r, kr2);                       // |rk| = |r| * kErrR (exact scaling by 1.0625 * 2^-23 up to 1 rounding)
+        const float2 dd = fma2(back, neg1, r);                // r - back, exact
+        const float E0 = fmaf(fabsf(b.x), w.e1, fabsf(rk.x));
+        const float E1 = fmaf(fabsf(b.y), w.e1, fabsf(rk.y));
+        okp[i] = slerp_certified_d(r.x, dd.x, E0) & slerp_certified_d(r.y, dd.y, E1);   // no short-circuit
+    }
+    if (!((okp[0] & okp[1]) & (okp[2] & okp[3]))) {
+        // about a fifth of the warp-vectors hold an uncertified element: that PAIR is recomputed with the reference's
+        // fp64 arithmetic (both halves -- cheaper than re-testing which one failed)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!okp[i]) {
+                const float2 a = __half22float2(ha[i]);
+                const float2 b = __half22float2(hb[i]);
+                ow[i] = slerp_exact_bits(a.x, b.x, s0, s1) | (slerp_exact_bits(a.y, b.y, s0, s1) << 16);
+            }
+        }
+    }
+    return o;
+}
+
+// fp16 -> fp64 in ONE conversion (cvt.f64.f16), both halves of a packed pair
+__device__ __forceinline__ void h2_to_d2(uint32_t packed, double& lo, double& hi) {
+    asm("{\n\t.reg .b16 l, h;\n\t"
+        "mov.b32 {l, h}, %2;\n\t"
+        "cvt.f64.f16 %0, l;\n\t"
+        "cvt.f64.f16 %1, h;\n\t}"
+        : "=d"(lo), "=d"(hi)
+        : "r"(packed));
+}
+template <typename T> struct ToD;
+template <> struct ToD<__half> {     // uint4 = 8 halves
+    __device__ static void cvt(const uint4& v, double (&d)[8]) {
+        h2_to_d2(v.x, d[0], d[1]);
+        h2_to_d2(v.y, d[2], d[3]);
+        h2_to_d2(v.z, d[4], d[5]);
+        h2_to_d2(v.w, d[6], d[7]);
+    }
+};
+template <> struct ToD<float> {      // uint4 = 4 floats
+    __device__ static void cvt(const uint4& v, double (&d)[4]) {
+        d[0] = (double)__uint_as_float(v.x);
+        d[1] = (double)__uint_as_float(v.y);
+        d[2] = (double)__uint_as_float(v.z);
+        d[3] = (double)__uint_as_float(v.w);
+    }
+};
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -227,12 +331,12 @@ slerp_stage_kernel(const T* __restrict__ p0, const T* __restrict__ p1, T* __rest
     const int nvec = mine / VE;
     double aa0 = 0.0, bb0 = 0.0, ab0 = 0.0, aa1 = 0.0, bb1 = 0.0, ab1 = 0.0;
     for (int v = threadIdx.x; v < nvec; v += THREADS) {
-        float fa[VE], fb[VE];
-        Vec<T>::unpack(reinterpret_cast<const uint4*>(sa)[v], fa);
-        Vec<T>::unpack(reinterpret_cast<const uint4*>(sb)[v], fb);
+        double da[VE], db[VE];
+        ToD<T>::cvt(reinterpret_cast<const uint4*>(sa)[v], da);
+        ToD<T>::cvt(reinterpret_cast<const uint4*>(sb)[v], db);
 #pragma unroll
         for (int e = 0; e < VE; e += 2) {
-            const double da0 = fa[e], db0 = fb[e], da1 = fa[e + 1], db1 = fb[e + 1];
+            const double da0 = da[e], db0 = db[e], da1 = da[e + 1], db1 = db[e + 1];
             aa0 = fma(da0, da0, aa0);
             bb0 = fma(db0, db0, bb0);
             ab0 = fma(da0, db0, ab0);
@@ -268,16 +372,13 @@ slerp_stage_kernel(const T* __restrict__ p0, const T* __restrict__ p1, T* __rest
     for (int v = threadIdx.x; v < nvec; v += THREADS) {
         const uint4 ua = reinterpret_cast<const uint4*>(sa)[v];
         const uint4 ub = reinterpret_cast<const uint4*>(sb)[v];
-        float fa[VE], fb[VE];
-        Vec<T>::unpack(ua, fa);
-        Vec<T>::unpack(ub, fb);
         uint4 o;
         if constexpr (!EXACT2 && sizeof(T) == 2) {
-            __half* oh = reinterpret_cast<__half*>(&o);
-#pragma unroll
-            for (int e = 0; e < VE; ++e) oh[e] = slerp_elem_h(fa[e], fb[e], w, s0, s1);
+            o = slerp_vec8_h(ua, ub, w, s0, s1);
         } else {
-            float fo[VE];
+            float fa[VE], fb[VE], fo[VE];
+            Vec<T>::unpack(ua, fa);
+            Vec<T>::unpack(ub, fb);
 #pragma unroll
             for (int e = 0; e < VE; ++e) fo[e] = slerp_elem(fa[e], fb[e], s0, s1);
             o = Vec<T>::pack(fo);
@@ -285,6 +386,155 @@ slerp_stage_kernel(const T* __restrict__ p0, const T* __restrict__ p1, T* __rest
         stg_stream(o_row + (int64_t)v * VE, o);
     }
     cluster_wait();
+}
+
+// ---- fast path B: two passes over global memory, the second served by L2 ------------------------
+// No on-chip staging at all: pass 1 streams the CTA's slice of both inputs from HBM (fp64 sums), pass 2 reads the
+// same slice again a few microseconds later -- by then it is resident in the 126 MB L2 (a whole launch keeps
+// < 148 SMs x 8 CTAs x 64 KiB = 76 MB in flight), so DRAM still sees 2 reads + 1 write per element.  With ~40
+// registers per thread and no shared-memory footprint, 8 CTAs are resident per SM and the long serial section
+// of each CTA (row reduction -> cluster exchange -> acos/sin weights -> second pass) is hidden by the others.
+// The weights are computed ONCE per row (rank 0, warp 0) and broadcast through distributed shared memory.
+struct RowWeights {
+    double s0, s1;
+    float s0h, s0l, s1h, s1l, e1, pad;
+};
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// first read of a line: it will be read once more by this CTA a few microseconds later -> keep it in L2
+template <bool HINT>
+__device__ __forceinline__ uint4 ldg_pass1(const void* p, uint64_t pol) {
+    uint4 r;
+    if constexpr (HINT)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+template <bool HINT>
+__device__ __forceinline__ void stg_hint(void* p, const uint4& v, uint64_t pol) {
+    if constexpr (HINT)
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x),
+                     "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                     : "memory");
+    else
+        stg_stream(p, v);
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// second (last) read of a line: tell L2 it is the first candidate for replacement
+template <bool HINT>
+__device__ __forceinline__ uint4 ldg_pass2(const void* p, uint64_t pol) {
+    uint4 r;
+    if constexpr (HINT)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+template <typename T, int THREADS, bool EXACT2, bool HINT, int OCC = 1280>
+__global__ void __launch_bounds__(THREADS, OCC / THREADS)
+slerp_l2_kernel(const T* __restrict__ p0, const T* __restrict__ p1, T* __restrict__ out, int64_t n, int slice,
+                int64_t stride0, int64_t stride1, int64_t stride_out, double fract,
+                const double* __restrict__ fract_rows) {
+    griddep_launch_dependents();
+    constexpr int VE = Vec<T>::N;
+    __shared__ double red[96];
+    __shared__ double cta_sum[3];
+    __shared__ RowWeights wbuf;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned crank = cluster.block_rank();
+    const unsigned csize = cluster.num_blocks();
+    const int64_t row = blockIdx.y;
+    const int64_t e0 = (int64_t)crank * slice;
+    const int mine = (int)max((int64_t)0, min((int64_t)slice, n - e0));
+    const int nvec = mine / VE;
+    const uint4* a4 = reinterpret_cast<const uint4*>(p0 + row * stride0 + e0);
+    const uint4* b4 = reinterpret_cast<const uint4*>(p1 + row * stride1 + e0);
+    uint4* o4 = reinterpret_cast<uint4*>(out + row * stride_out + e0);
+    griddep_wait();
+
+    // ---- pass 1 (HBM): fp64 row sums
+    const uint64_t pol_keep = l2_policy_evict_last();
+    double aa0 = 0.0, bb0 = 0.0, ab0 = 0.0, aa1 = 0.0, bb1 = 0.0, ab1 = 0.0;
+#pragma unroll 4
+    for (int v = threadIdx.x; v < nvec; v += THREADS) {
+        double da[VE], db[VE];
+        ToD<T>::cvt(ldg_pass1<HINT>(a4 + v, pol_keep), da);
+        ToD<T>::cvt(ldg_pass1<HINT>(b4 + v, pol_keep), db);
+#pragma unroll
+        for (int e = 0; e < VE; e += 2) {
+            aa0 = fma(da[e], da[e], aa0);
+            bb0 = fma(db[e], db[e], bb0);
+            ab0 = fma(da[e], db[e], ab0);
+            aa1 = fma(da[e + 1], da[e + 1], aa1);
+            bb1 = fma(db[e + 1], db[e + 1], bb1);
+            ab1 = fma(da[e + 1], db[e + 1], ab1);
+        }
+    }
+    double aa = aa0 + aa1, bb = bb0 + bb1, ab = ab0 + ab1;
+    block_reduce3<THREADS>(aa, bb, ab, red);
+    if (threadIdx.x == 0) {
+        cta_sum[0] = aa;
+        cta_sum[1] = bb;
+        cta_sum[2] = ab;
+    }
+    cluster_arrive();
+    cluster_wait();
+    if (crank == 0 && threadIdx.x < 32) {
+        // fixed-order combine, then the scalar fp64 section once per row
+        double taa = 0.0, tbb = 0.0, tab = 0.0;
+        for (unsigned r = 0; r < csize; ++r) {
+            const double* remote = cluster.map_shared_rank(cta_sum, r);
+            taa += remote[0];
+            tbb += remote[1];
+            tab += remote[2];
+        }
+        const double f = fract_rows ? fract_rows[row] : fract;
+        RowWeights rw;
+        slerp_weights(taa, tbb, tab, f, rw.s0, rw.s1);
+        const SplitW w(rw.s0, rw.s1);
+        rw.s0h = w.s0h; rw.s0l = w.s0l; rw.s1h = w.s1h; rw.s1l = w.s1l; rw.e1 = w.e1; rw.pad = 0.f;
+        if (threadIdx.x < csize) *cluster.map_shared_rank(&wbuf, threadIdx.x) = rw;
+    }
+    cluster_arrive();
+    cluster_wait();
+    const double s0 = wbuf.s0, s1 = wbuf.s1;
+    SplitW w;
+    w.s0h = wbuf.s0h; w.s0l = wbuf.s0l; w.s1h = wbuf.s1h; w.s1l = wbuf.s1l; w.e1 = wbuf.e1;
+
+    // ---- pass 2 (L2): axpby, 128-bit coalesced streaming stores
+    const uint64_t pol = l2_policy_evict_first();
+#pragma unroll 2
+    for (int v = threadIdx.x; v < nvec; v += THREADS) {
+        const uint4 ua = ldg_pass2<HINT>(a4 + v, pol);
+        const uint4 ub = ldg_pass2<HINT>(b4 + v, pol);
+        uint4 o;
+        if constexpr (!EXACT2 && sizeof(T) == 2) {
+            o = slerp_vec8_h(ua, ub, w, s0, s1);
+        } else {
+            float fa[VE], fb[VE], fo[VE];
+            Vec<T>::unpack(ua, fa);
+            Vec<T>::unpack(ub, fb);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) fo[e] = slerp_elem(fa[e], fb[e], s0, s1);
+            o = Vec<T>::pack(fo);
+        }
+        stg_hint<HINT>(o4 + v, o, pol);
+    }
 }
 
 }  // namespace lbmix

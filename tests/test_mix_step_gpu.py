@@ -124,3 +124,38 @@ def test_cfg_euler_step_bit_exact(turbo, hw):
         out1 = ops.cfg_euler_step(x.cuda(), eps[:1].contiguous().cuda(), 0.0, h(sigma), dt, sup,
                                   noise=None if noise is None else noise.cuda()).cpu()
         assert torch.equal(out1, ref_nocfg)
+
+
+def test_slerp_certified_fp32_path_equals_exact_fp64_path(monkeypatch):
+    """K1 pass 2 evaluates p0*s0 + p1*s1 in split-weight fp32 and certifies the fp16 rounding, falling back to the
+    reference's fp64 arithmetic per element (csrc/mix_kernels.cuh).  A/B it against the all-fp64 evaluation
+    (LB_SLERP_EXACT=1) on adversarial value families, and against the oracle."""
+    from latentblending_b200 import ops
+    from oracle import mixing
+    g = torch.Generator().manual_seed(11)
+    n = 4 * 128 * 128
+    fam = []
+    a, b = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    fam.append((a, b))                                             # typical latents
+    fam.append((a * 3e-6, b * 3e-6))                               # fp16 subnormals in and out
+    fam.append((a * 9000, b * 9000))                               # near the fp16 overflow threshold
+    fam.append((a, a.clone()))                                     # identical rows (dot clamp)
+    fam.append((a, -a * 1.0009765625))                             # near-antipodal: heavy cancellation
+    z = a.clone(); z[torch.rand(n, generator=g) < 0.75] = 0
+    fam.append((z, b * (torch.rand(n, generator=g) < 0.5)))        # exact zeros
+    e = torch.randint(-20, 10, (n,), generator=g).float()
+    fam.append((a * torch.exp2(e), b * torch.exp2(e.flip(0))))     # 30 binades of magnitude
+    fam.append((a * 0.01, b * 100))
+    p0 = torch.stack([f[0] for f in fam]).half()
+    p1 = torch.stack([f[1] for f in fam]).half()
+    for fract in (0.0, 0.25, 0.5, 0.8137, 1.0):
+        monkeypatch.delenv("LB_SLERP_EXACT", raising=False)
+        fast = ops.slerp_rows(p0.cuda(), p1.cuda(), fract).cpu()
+        monkeypatch.setenv("LB_SLERP_EXACT", "1")
+        exact = ops.slerp_rows(p0.cuda(), p1.cuda(), fract).cpu()
+        monkeypatch.delenv("LB_SLERP_EXACT", raising=False)
+        assert torch.equal(fast.view(torch.int16), exact.view(torch.int16)), \
+            f"fract {fract}: {(fast.view(torch.int16) != exact.view(torch.int16)).sum().item()} mismatches"
+        for r in (0, 2, 6):
+            ref = mixing.interpolate_spherical(p0[r], p1[r], fract)
+            assert torch.equal(fast[r].view(torch.int16), ref.view(torch.int16)), f"row {r} fract {fract}"
