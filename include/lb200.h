@@ -111,8 +111,11 @@ typedef struct lb_gemm_desc {
     const void* bias2; int64_t bias2_ld;
     const void* res; int64_t res_ld;
     void* out; int64_t out_ld;
-    int32_t mode;
+    int32_t mode;     /* low byte: 0 = linear epilogue, 1 = GEGLU; flags: LB_GEMM_STATIC_W */
 } lb_gemm_desc;
+/* mode flag: `w` is not written by the kernel that precedes this one on the stream (true for model weights, false
+ * when an activation is passed as the B operand): its first tiles may be fetched before the previous kernel ends. */
+#define LB_GEMM_STATIC_W 0x100
 int lb_gemm(lb_ctx* ctx, const lb_gemm_desc* desc, void* stream);
 
 /* ---- K8: fused attention, head_dim 64 ----------------------------------------

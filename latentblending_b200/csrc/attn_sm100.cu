@@ -6,14 +6,20 @@
 // Q,K,V slices of one fused-QKV activation) and cross-attention to the 77 text
 // tokens (K,V slices of a [B,77,2C] projection).  fp16 in, fp32 softmax, fp16 out.
 //
-// One CTA = 128 query rows of one (batch, head); two CTAs per SM so one CTA's
-// softmax overlaps the other's MMAs.  Per 128-key tile:
+// One CTA = 256 query rows (two 128-row halves) of one (batch, head).  Per 128-key tile and half:
 //   S = Q K^T   tcgen05.mma M128 N128 K64, Q/K K-major 128B-swizzled TMA tiles, S in TMEM
-//   softmax     warps 2-5, one query row per thread: tcgen05.ld S, online max/sum in
-//               the exp2 domain, P (fp16) written to smem in the UMMA K-major layout
-//   O_j = P V   tcgen05.mma M128 N64 K128, V consumed MN-major straight from its TMA tile
-//   O = alpha*O + O_j in registers (fp32), normalised by the row sum at the end.
-// Bound: tensor pipe / MUFU.EX2; algorithmic FLOPs = 4*Sq*Skv*64 per head.
+//   softmax     one query row per thread (two warpgroups, one per half, ping-pong against the MMA issuer):
+//               pass 1 row max, pass 2 p = 2^(s*scale - m) -> fp16 P tile in smem (UMMA K-major layout);
+//               TMEM loads are software-pipelined (chunk c+1 in flight while chunk c is processed)
+//   O += P V    tcgen05.mma M128 N64 K128 ACCUMULATING IN TMEM, V consumed MN-major from its TMA tile
+// The running maximum is lazy: O (in TMEM) and the row sum are rescaled only when a row's maximum grows by more
+// than 2^8 (then p <= 256, harmless in fp16/fp32); after the first tiles that almost never happens, so the
+// softmax threads neither hold O in registers nor touch it per tile.  S(j+1) is issued behind P V(j) on the
+// in-order tensor pipe, so observing S(j) complete implies P V(j-1) has completed: the rare rescale needs no
+// extra barrier.  O is normalised by the row sum once, at the end.
+// Bound: tensor pipe / MUFU.EX2 (16/clk/SM): at head dim 64 one exp feeds only 256 tensor FLOPs, so MUFU alone caps
+// the tensor pipe at 50 %; every 4th pair of exps runs as a packed-fp32 polynomial on the FMA pipe instead.
+// Algorithmic FLOPs = 4*Sq*Skv*64 per head.
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
     uint64_t* v_empty = bars + 7;    // [2]
     uint64_t* s_full = bars + 9;     // [2] per half
     uint64_t* p_ready = bars + 11;   // [2]
-    uint64_t* o_full = bars + 13;    // [2]
+    uint64_t* o_final = bars + 13;   // [2] last P V of each half has completed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
             mbar_init(&v_empty[i], 1);
             mbar_init(&s_full[i], 1);
             mbar_init(&p_ready[i], 4);
-            mbar_init(&o_full[i], 1);
+            mbar_init(&o_final[i], 1);
         }
         fence_mbar_init();
     }
@@ -130,14 +136,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
             }
             __syncwarp();
         };
-        auto issue_pv = [&](int half, int st, uint64_t* also_commit) {
+        auto issue_pv = [&](int half, int st, bool first, bool last, uint64_t* also_commit) {
             if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < kBKV / 16; ++k)
                     umma_f16(tmem_base + 256 + half * 64,
                              make_smem_desc_sw128(p_addr + half * kPBytes + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                             make_smem_desc_sw128(v_addr + st * kTileBytes + k * 2048, 1024, 1024), idesc_pv, k != 0);
-                umma_commit(&o_full[half]);
+                             make_smem_desc_sw128(v_addr + st * kTileBytes + k * 2048, 1024, 1024), idesc_pv,
+                             (first && k == 0) ? 0u : 1u);      // O accumulates in TMEM across KV tiles
+                if (last) umma_commit(&o_final[half]);
                 if (also_commit) umma_commit(also_commit);
             }
             __syncwarp();
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
             mbar_wait(&v_full[st], kvph, p.err_flag, 16);
             mbar_wait(&p_ready[0], ph, p.err_flag, 15);
             tc_fence_after();
-            issue_pv(0, st, nullptr);
+            issue_pv(0, st, j == 0, !more, nullptr);
             if (more) {
                 mbar_wait(&k_full[stn], kvphn, p.err_flag, 14);
                 tc_fence_after();
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
             }
             mbar_wait(&p_ready[1], ph, p.err_flag, 15);
             tc_fence_after();
-            issue_pv(1, st, &v_empty[st]);
+            issue_pv(1, st, j == 0, !more, &v_empty[st]);
             if (more) issue_qk(1, stn, &k_empty[stn]);
         }
     } else if (warp >= 4) {
@@ -174,126 +181,130 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
         const uint32_t tmem_S = tmem_base + half * 128 + lane_off;
         const uint32_t tmem_O = tmem_base + 256 + half * 64 + lane_off;
         uint8_t* sPh = sP + half * kPBytes;
-        float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
-        float o_acc[kD];
-#pragma unroll
-        for (int i = 0; i < kD; ++i) o_acc[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;     // m_run in the scaled (log2) domain
         const float sc = p.scale_log2;
         for (int j = 0; j < nkv; ++j) {
             const uint32_t ph = j & 1;
             const int kv_valid = min(kBKV, p.Skv - j * kBKV);
             mbar_wait(&s_full[half], ph, p.err_flag, 17);
             tc_fence_after();
-            // pass 1: row max (3-input max: 64 instructions for 128 values)
+            // ---- pass 1: row max (3-input max), TMEM loads double-buffered
             float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_S + c * 32, v);
+            {
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32b_x32(tmem_S, va);
                 tmem_ld_wait();
-                if (kv_valid == kBKV) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-                } else {
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t (&cur)[32] = (c & 1) ? vb : va;
+                    uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+                    if (c < 3) tmem_ld_32x32b_x32(tmem_S + (c + 1) * 32, nxt);
+                    if (kv_valid == kBKV) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-                }
-            }
-            const float m_new = fmaxf(m_run, mx * sc);
-            const float alpha = ex2_approx(m_run - m_new);   // first tile: 2^(-inf) = 0
-            // fold the PREVIOUS tile's P V into the running output while this tile's MMAs are in flight
-            if (j > 0) {
-                mbar_wait(&o_full[half], ph ^ 1, p.err_flag, 18);
-                tc_fence_after();
+                        for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+                    } else {
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tmem_O + c * 32, v);
-                    tmem_ld_wait();
-                    const float2 a2 = make_float2(alpha_prev, alpha_prev);
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float2 r2 = ffma2(make_float2(o_acc[c * 32 + i], o_acc[c * 32 + i + 1]), a2,
-                                                make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-                        o_acc[c * 32 + i] = r2.x;
-                        o_acc[c * 32 + i + 1] = r2.y;
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(cur[i]));
                     }
+                    if (c < 3) tmem_ld_wait();
                 }
             }
-            alpha_prev = alpha;
+            // ---- lazy maximum: rescale O / l only when some row of this warp outgrew its reference by 2^8
+            const float m_cand = mx * sc;
+            if (__any_sync(0xffffffffu, m_cand - m_run > 8.0f)) {      // j == 0: m_run = -inf -> always
+                const float m_new = fmaxf(m_run, m_cand);
+                const float alpha = ex2_approx(m_run - m_new);          // first tile: 2^(-inf) = 0
+                if (j > 0) {
+                    // P V(j-1) has completed: S(j) was issued behind it on the in-order tensor pipe
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_O + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        tmem_st_32x32b_x32(tmem_O + c * 32, v);
+                    }
+                    tmem_st_wait();
+                }
+                l_run *= alpha;
+                m_run = m_new;
+            }
             float2 psum2 = make_float2(0.f, 0.f);
-            const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_new, -m_new);
-            // pass 2: p = 2^(s*sc - m_new) -> fp16 -> smem (K-major, 128B swizzle: 16B chunk ^= row & 7).
+            const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_run, -m_run);
+            // ---- pass 2: p = 2^(s*sc - m_run) -> fp16 -> smem (K-major, 128B swizzle: 16B chunk ^= row & 7).
             // Packed fp32 FMAs; every 4th pair takes the polynomial 2^x so MUFU.EX2 (16/clk/SM) is not the only exp unit.
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_S + c * 32, v);
+            {
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32b_x32(tmem_S, va);
                 tmem_ld_wait();
-                uint8_t* prow = sPh + (c >> 1) * 16384 + r * 128;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 pk;
-                    __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t (&cur)[32] = (c & 1) ? vb : va;
+                    uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+                    if (c < 3) tmem_ld_32x32b_x32(tmem_S + (c + 1) * 32, nxt);
+                    uint8_t* prow = sPh + (c >> 1) * 16384 + r * 128;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int col = c * 32 + g * 8 + 2 * i;
-                        const float2 x2 = ffma2(make_float2(__uint_as_float(v[g * 8 + 2 * i]),
-                                                            __uint_as_float(v[g * 8 + 2 * i + 1])), sc2, nm2);
-                        float2 e2;
-                        if (i == 3) {
-                            e2.x = ex2_poly(x2.x);
-                            e2.y = ex2_poly(x2.y);
-                        } else {
-                            e2.x = ex2_approx(x2.x);
-                            e2.y = ex2_approx(x2.y);
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 pk;
+                        __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int col = c * 32 + g * 8 + 2 * i;
+                            const float2 x2 = ffma2(make_float2(__uint_as_float(cur[g * 8 + 2 * i]),
+                                                                __uint_as_float(cur[g * 8 + 2 * i + 1])), sc2, nm2);
+                            float2 e2;
+                            if (i == 3) {
+                                e2 = ex2_poly2(x2);
+                            } else {
+                                e2.x = ex2_approx(x2.x);
+                                e2.y = ex2_approx(x2.y);
+                            }
+                            if (kv_valid != kBKV) {
+                                if (col >= kv_valid) e2.x = 0.f;
+                                if (col + 1 >= kv_valid) e2.y = 0.f;
+                            }
+                            psum2 = fadd2(psum2, e2);
+                            ph2[i] = __floats2half2_rn(e2.x, e2.y);
                         }
-                        if (kv_valid != kBKV) {
-                            if (col >= kv_valid) e2.x = 0.f;
-                            if (col + 1 >= kv_valid) e2.y = 0.f;
-                        }
-                        psum2 = fadd2(psum2, e2);
-                        ph2[i] = __floats2half2_rn(e2.x, e2.y);
+                        const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
+                        *reinterpret_cast<uint4*>(prow + chunk * 16) = pk;
                     }
-                    const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
-                    *reinterpret_cast<uint4*>(prow + chunk * 16) = pk;
+                    if (c < 3) tmem_ld_wait();
                 }
             }
-            const float psum = psum2.x + psum2.y;
-            l_run = l_run * alpha + psum;
-            m_run = m_new;
+            l_run += psum2.x + psum2.y;
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[half]);
         }
-        // last tile's P V
-        mbar_wait(&o_full[half], (nkv - 1) & 1, p.err_flag, 19);
+        // ---- output: O / l
+        mbar_wait(&o_final[half], 0, p.err_flag, 19);
         tc_fence_after();
+        const int q = q0 + half * 128 + r;
+        const float inv = 1.0f / l_run;
+        __half* dst = p.out + ((long long)b * p.Sq + q) * p.ldo + head * kD;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_O + c * 32, v);
             tmem_ld_wait();
+            if (q < p.Sq) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
-        }
-        tc_fence_before();
-        const int q = q0 + half * 128 + r;
-        if (q < p.Sq) {
-            const float inv = 1.0f / l_run;
-            __half* dst = p.out + ((long long)b * p.Sq + q) * p.ldo + head * kD;
+                for (int g = 0; g < 4; ++g) {
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                uint4 o;
-                __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    oh[i] = __floats2half2_rn(o_acc[g * 8 + 2 * i] * inv, o_acc[g * 8 + 2 * i + 1] * inv);
-                *reinterpret_cast<uint4*>(dst + g * 8) = o;
+                    for (int i = 0; i < 4; ++i)
+                        oh[i] = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * i]) * inv,
+                                                  __uint_as_float(v[g * 8 + 2 * i + 1]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
+                }
             }
         }
+        tc_fence_before();
     }
     tc_fence_before();
     __syncthreads();

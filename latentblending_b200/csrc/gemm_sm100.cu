@@ -10,15 +10,22 @@
 // by (dy,dx) with hardware zero fill at the borders -- no im2col buffer), and
 // the resnet shortcut folded in as an extra K-segment from a second tensor.
 //
-// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+// Structure (one CTA per SM, persistent over output tiles, 320 threads):
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor 4D (A) / 2D (W) into a
 //              STAGES-deep 128B-swizzled smem ring, mbarrier full/empty pairs
 //   warp 1   : MMA issuer    -- one thread issues tcgen05.mma (M=128, N=BN,
 //              K=16, fp16 in / fp32 accumulate in TMEM), tcgen05.commit frees
 //              smem slots and publishes the accumulator
-//   warps 2-5: epilogue      -- tcgen05.ld TMEM->registers, + bias / per-batch
-//              bias (time embedding) / residual, or GEGLU, fp16 store;
-//              double-buffered accumulators overlap it with the next tile's MMAs
+//   warps 2-9: epilogue      -- tcgen05.ld TMEM->registers, + bias / per-batch
+//              bias (time embedding) / residual, or GEGLU, fp16 store; two warps
+//              per TMEM lane quadrant split the tile's columns (the GEGLU / residual
+//              epilogue of one warp per scheduler was as long as the tile's MMAs);
+//              residual rows are prefetched while the accumulator is still being
+//              produced; double-buffered accumulators overlap the epilogue with the
+//              next tile's MMAs
+// Weight (B operand) tiles of the first pipeline stages are requested BEFORE
+// griddepcontrol.wait when the caller marks the weights static (LB_GEMM_STATIC_W):
+// their HBM latency hides behind the tail of the previous kernel.
 // Bound: tensor pipe; algorithmic FLOPs = 2*M*N*K.
 #include "gemm_sm100.cuh"
 #include <stdlib.h>
@@ -31,7 +38,8 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kThreadsGemm = 192;
+constexpr int kThreadsGemm = 320;
+constexpr int kEpiWarps = 8;
 constexpr int kABytes = kBM * kBK * 2;  // 16 KiB
 
 template <int BN> struct Cfg {
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4 * CL);   // pair: the leader waits for both CTAs' epilogue warps
+            mbar_init(&tmem_empty[a], kEpiWarps * CL);   // pair: the leader waits for both CTAs' epilogue warps
         }
         fence_mbar_init();
     }
@@ -102,13 +110,29 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
     if (CL == 2) cluster_sync_all();          // peer barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();                               // everything above overlapped the previous kernel; its outputs are visible now
 
     // tile index space: (m-group, n) with CL vertically adjacent M tiles per group
     const int m_groups = (p.tiles_m + CL - 1) / CL;
     const int num_tiles = m_groups * p.tiles_n;
     const int tile0 = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+
+    // Static weights do not depend on the previous grid: request the B tiles of the first ring stages now, while
+    // that grid is still finishing (the A tiles of the same stages follow after griddepcontrol.wait).
+    int early_kb = 0;
+    if (CL == 1 && p.static_w && !(p.debug & 1) && tile0 < num_tiles)
+        early_kb = p.total_kb < C::stages ? p.total_kb : C::stages;
+    if (warp == 0 && early_kb > 0) {
+        if (elect_one()) {
+            const int n_tile = tile0 / m_groups;
+            for (int kb = 0; kb < early_kb; ++kb) {
+                mbar_expect_tx(&full[kb], C::stage_bytes);
+                tma_load_2d(smem_b + kb * C::b_bytes, &p.tmB, &full[kb], kb * kBK, n_tile * BN);
+            }
+        }
+        __syncwarp();
+    }
+    pdl_wait();                               // everything above overlapped the previous kernel; its outputs are visible now
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
@@ -135,6 +159,9 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
                         tma_load_4d_2sm(smem_a + stage * kABytes, ma, lead_full, kb * kBK, x0 + dx, y0 + dy, b0);
                         tma_load_2d_2sm(smem_b + stage * C::b_bytes, &p.tmBh, lead_full, kb_global * kBK,
                                         n_tile * BN + (int)crank * (BN / 2));
+                    } else if (tile == tile0 && kb_global < early_kb) {
+                        // expect_tx and the weight tile were issued before griddepcontrol.wait
+                        tma_load_4d(smem_a + stage * kABytes, ma, &full[stage], kb * kBK, x0 + dx, y0 + dy, b0);
                     } else {
                         mbar_expect_tx(&full[stage], C::stage_bytes);
                         tma_load_4d(smem_a + stage * kABytes, ma, &full[stage], kb * kBK, x0 + dx, y0 + dy, b0);
@@ -185,10 +212,12 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 2) {
-        // ===================== epilogue =====================
+        // ===================== epilogue (8 warps: two per TMEM lane quadrant, splitting the columns) =====================
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int part = (warp - 2) >> 2;       // 0: first half of the tile's column chunks, 1: second half
         const int r = q * 32 + lane;            // accumulator row inside the tile
         const int ww = r % p.tw, hh = (r / p.tw) % p.th, bb = r / (p.tw * p.th);
+        const int mode = p.mode;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -198,46 +227,69 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
             const int b = (m_tile / (p.tiles_x * p.tiles_y)) * p.tb + bb;
             const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B) && (m_tile < p.tiles_m);
             const long long row = ((long long)b * p.H + y) * p.W + x;
-            mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 4);
-            tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            if (p.mode == 0) {
+            if (mode == 0) {
+                constexpr int NCH = BN / 32;                 // 32-column chunks of the tile
+                constexpr int NCH0 = (NCH + 1) / 2;          // chunks of part 0
+                constexpr int NPER = NCH0;                   // max chunks per warp
+                const int c_begin = part ? NCH0 : 0, c_end = part ? NCH : NCH0;
                 const int n_base = n_tile * BN;
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_addr + c * 32, v);
-                    tmem_ld_wait();
-                    const int n0 = n_base + c * 32;
-                    if (row_ok && n0 < p.N) {
+                const __half* res_row = p.res ? p.res + row * p.ldr : nullptr;
+                // residual of the first chunk: requested BEFORE the accumulator is complete (overlaps the MMAs)
+                uint4 rnext[4];
+                auto load_res = [&](int c, uint4 (&dst)[4]) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const int n = n0 + g * 8;
-                            if (n < p.N) {      // N is a multiple of 8 (checked on the host)
-                                float acc8[8];
+                    for (int g = 0; g < 4; ++g) {
+                        const int n = n_base + c * 32 + g * 8;
+                        dst[g] = (res_row && row_ok && n < p.N) ? *reinterpret_cast<const uint4*>(res_row + n)
+                                                               : make_uint4(0, 0, 0, 0);
+                    }
+                };
+                if (c_begin < c_end) load_res(c_begin, rnext);
+                mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 4);
+                tc_fence_after();
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) acc8[j] = __uint_as_float(v[g * 8 + j]);
-                                float t8[8];
-                                if (p.bias) {
-                                    unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + n)), t8);
+                for (int i = 0; i < NPER; ++i) {
+                    const int c = c_begin + i;
+                    if (c < c_end) {                    // warp-uniform
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(t_addr + c * 32, v);
+                        uint4 rcur[4];
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) acc8[j] += t8[j];
+                        for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+                        if (c + 1 < c_end) load_res(c + 1, rnext);   // in flight while this chunk is processed
+                        tmem_ld_wait();
+                        const int n0 = n_base + c * 32;
+                        if (row_ok && n0 < p.N) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int n = n0 + g * 8;
+                                if (n < p.N) {      // N is a multiple of 8 (checked on the host)
+                                    float acc8[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) acc8[j] = __uint_as_float(v[g * 8 + j]);
+                                    float t8[8];
+                                    if (p.bias) {
+                                        unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + n)), t8);
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) acc8[j] += t8[j];
+                                    }
+                                    if (p.bias2) {
+                                        unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias2 + (long long)b * p.bias2_ld + n)), t8);
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) acc8[j] += t8[j];
+                                    }
+                                    if (p.res) {
+                                        unpack8(rcur[g], t8);
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) acc8[j] += t8[j];
+                                    }
+                                    uint4 o;
+                                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc8[2 * j], acc8[2 * j + 1]);
+                                    *reinterpret_cast<uint4*>(p.out + row * p.ldo + n) = o;
                                 }
-                                if (p.bias2) {
-                                    unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias2 + (long long)b * p.bias2_ld + n)), t8);
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) acc8[j] += t8[j];
-                                }
-                                if (p.res) {
-                                    unpack8(*reinterpret_cast<const uint4*>(p.res + row * p.ldr + n), t8);
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) acc8[j] += t8[j];
-                                }
-                                uint4 o;
-                                __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc8[2 * j], acc8[2 * j + 1]);
-                                *reinterpret_cast<uint4*>(p.out + row * p.ldo + n) = o;
                             }
                         }
                     }
@@ -246,10 +298,15 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
                 // GEGLU: tile columns [0,BN/2) are "value", [BN/2,BN) the matching "gate" (weights are
                 // row-interleaved per tile on the host); out = (v+bv) * gelu(g+bg), BN/2 outputs per tile.
                 constexpr int HN = BN / 2;
+                constexpr int NCH = HN / 32;
+                constexpr int NCH0 = (NCH + 1) / 2;
+                const int c_begin = part ? NCH0 : 0, c_end = part ? NCH : NCH0;
                 const int o_base = n_tile * HN;        // output column base
                 const int a_base = n_tile * BN;        // accumulator (bias) column base
+                mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 4);
+                tc_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < HN / 32; ++c) {
+                for (int c = c_begin; c < c_end; ++c) {
                     uint32_t vv[32], vg[32];
                     tmem_ld_32x32b_x32(t_addr + c * 32, vv);
                     tmem_ld_32x32b_x32(t_addr + HN + c * 32, vg);
@@ -424,7 +481,7 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
     p.tiles_m = p.tiles_x * p.tiles_y * tiles_b;
     // --- N tiling
     int bn;
-    if (d.mode == 1) {
+    if ((d.mode & 0xff) == 1) {
         bn = 128;
         LB_REQUIRE(d.N % 128 == 0, "gemm: GEGLU needs N %% 128 == 0 (got %d)", d.N);
     } else if (d.N % 256 == 0 && (int64_t)p.tiles_m * (d.N / 256) >= 2 * ctx->sm_count) bn = 256;
@@ -435,7 +492,8 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
     plan->bn = bn;
     p.tiles_n = (int)lb_ceil_div(d.N, bn);
     p.N = d.N;
-    p.mode = d.mode;
+    p.mode = d.mode & 0xff;
+    p.static_w = (d.mode & LB_GEMM_STATIC_W) ? 1 : 0;
     // --- K segments
     int ns = 0, total = 0;
     if (d.taps == 9) {

@@ -14,7 +14,7 @@ struct GemmDesc {
     const void* bias2; int64_t bias2_ld;
     const void* res; int64_t res_ld;
     void* out; int64_t out_ld;
-    int32_t mode;   // 0 linear epilogue, 1 GEGLU (N accumulators -> N/2 outputs)
+    int32_t mode;   // low byte: 0 linear epilogue, 1 GEGLU (N accumulators -> N/2 outputs); | LB_GEMM_STATIC_W
 };
 
 constexpr int kGemmMaxSegs = 12;
@@ -31,6 +31,7 @@ struct alignas(64) GemmParams {
     int tiles_x, tiles_y, tiles_m, tiles_n;
     int N;
     int mode;
+    int static_w;  // weights may be fetched before griddepcontrol.wait (LB_GEMM_STATIC_W)
     __half* out; long long ldo;
     const __half* bias;
     const __half* bias2; long long bias2_ld;

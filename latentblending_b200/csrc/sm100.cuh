@@ -209,6 +209,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t (&r)
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: this warp's 32 lanes x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- packed fp32 / fast math (sm_100: two fp32 lanes per instruction) -----------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -247,6 +260,23 @@ __device__ __forceinline__ float ex2_poly(float x) {
     pl = fmaf(pl, f, 0.693147181f);
     pl = fmaf(pl, f, 1.0f);
     return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
+
+// two lanes of 2^x at once: the range split and the polynomial run as packed fp32 (x >= -126 after the clamp)
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+    x.x = fmaxf(x.x, -126.0f);
+    x.y = fmaxf(x.y, -126.0f);
+    const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+    const float2 t = fadd2(x, magic);                                   // 1.5 * 2^23: low mantissa bits = round(x)
+    const float2 f = ffma2(fadd2(t, nmagic), make_float2(-1.0f, -1.0f), x);   // x - round(x), in [-0.5, 0.5]
+    float2 pl = ffma2(f, make_float2(0.009618129f, 0.009618129f), make_float2(0.055504109f, 0.055504109f));
+    pl = ffma2(pl, f, make_float2(0.240226507f, 0.240226507f));
+    pl = ffma2(pl, f, make_float2(0.693147181f, 0.693147181f));
+    pl = ffma2(pl, f, make_float2(1.0f, 1.0f));
+    float2 r;
+    r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(t.x) << 23));
+    r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(t.y) << 23));
+    return r;
 }
 
 // ---- descriptors ------------------------------------------------------------------------

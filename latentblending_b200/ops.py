@@ -92,7 +92,7 @@ def _p(t):
 
 
 def gemm(a0, w, N, B, H, W, taps=1, a0_c=None, a1=None, a1_c=None, bias=None, bias2=None, res=None, out=None,
-         mode=0, out_cols=None):
+         mode=0, out_cols=None, static_w=False):
     """Tensor-core GEMM / implicit-GEMM conv (lb_gemm).  a0: NHWC activation viewed as
     [B*H*W, >=a0_c] (row stride = a0.stride(0)); w: [N, K] packed weights."""
     dev = _dev(a0)
@@ -112,7 +112,7 @@ def gemm(a0, w, N, B, H, W, taps=1, a0_c=None, a1=None, a1_c=None, bias=None, bi
         d.bias2, d.bias2_ld = _p(bias2), bias2.stride(0)
     if res is not None:
         d.res, d.res_ld = _p(res), res.stride(-2)
-    d.out, d.out_ld, d.mode = _p(out), out.stride(-2), mode
+    d.out, d.out_ld, d.mode = _p(out), out.stride(-2), mode | (_cabi.GEMM_STATIC_W if static_w else 0)
     check(_cabi.load().lb_gemm(ctx(dev), d, stream_ptr()), "lb_gemm")
     return out
 

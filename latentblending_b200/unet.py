@@ -26,7 +26,7 @@ from typing import Tuple
 import torch
 
 from . import _cabi
-from ._cabi import (OP_ATTENTION, OP_CONV_IN, OP_CONV_OUT, OP_EMBED_INPUTS, OP_GEMM, OP_GROUPNORM, OP_IM2COL_S2,
+from ._cabi import (GEMM_STATIC_W, OP_ATTENTION, OP_CONV_IN, OP_CONV_OUT, OP_EMBED_INPUTS, OP_GEMM, OP_GROUPNORM, OP_IM2COL_S2,
                     OP_LATENT_PREP, OP_LAYERNORM, OP_LINEAR_SMALL, OP_POSTPROCESS_U8, OP_SOFTMAX_ROWS, OP_UPSAMPLE2X,
                     Op, check, ctx, stream_ptr)
 
@@ -79,7 +79,10 @@ class Program:
 
     # -- op emitters (mirror latentblending_b200.ops, but record instead of launching) --------
     def gemm(self, a0, w, N, B, H, W, out, taps=1, a0_c=None, a1=None, a1_c=None, bias=None, bias2=None, res=None,
-             mode=0):
+             mode=0, static_w=True):
+        """``static_w``: ``w`` holds model weights (not written by the preceding op), so the kernel may fetch its
+        first tiles before the preceding kernel has finished (LB_GEMM_STATIC_W).  Pass False when an activation
+        is used as the B operand."""
         d = self._new(OP_GEMM).u.gemm
         d.a0, d.a0_ld, d.a0_c = _p(a0), a0.stride(0), (a0.shape[1] if a0_c is None else a0_c)
         if a1 is not None:
@@ -91,7 +94,7 @@ class Program:
             d.bias2, d.bias2_ld = _p(bias2), bias2.stride(0)
         if res is not None:
             d.res, d.res_ld = _p(res), res.stride(0)
-        d.out, d.out_ld, d.mode = _p(out), out.stride(0), mode
+        d.out, d.out_ld, d.mode = _p(out), out.stride(0), mode | (GEMM_STATIC_W if static_w else 0)
         self.hold(a0, w, a1, bias, bias2, res, out)
 
     def attention(self, q, k, v, out, B, heads, Sq, Skv, q_col0=0, k_col0=0, v_col0=0, scale=0.125):

@@ -137,12 +137,12 @@ class _VAELowering:
         qk = torch.empty(S, 2 * C0, **f16)
         P.gemm(hn, Wt["attn.qk.w"], 2 * C0, 1, 1, S, qk, bias=Wt["attn.qk.b"])
         vT = torch.empty(C0, S, **f16)
-        P.gemm(Wt["attn.v.w"], hn, S, 1, 1, C0, vT)                       # V^T = Wv hn^T
+        P.gemm(Wt["attn.v.w"], hn, S, 1, 1, C0, vT, static_w=False)                       # V^T = Wv hn^T
         scores = torch.empty(S, S, **f16)
-        P.gemm(qk[:, :C0], qk[:, C0:], S, 1, 1, S, scores)               # (scaled q) k^T
+        P.gemm(qk[:, :C0], qk[:, C0:], S, 1, 1, S, scores, static_w=False)               # (scaled q) k^T
         P.softmax_rows(scores, scores)
         att = sc("h1", S, C0)
-        P.gemm(scores, vT, C0, 1, 1, S, att)                              # P V
+        P.gemm(scores, vT, C0, 1, 1, S, att, static_w=False)                              # P V
         x3 = torch.empty(S, C0, **f16)
         P.gemm(att, Wt["attn.out.w"], C0, 1, 1, S, x3, bias=Wt["attn.out.b"], res=x2)
         x4 = torch.empty(S, C0, **f16)
