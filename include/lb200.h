@@ -141,6 +141,9 @@ int lb_attention(lb_ctx* ctx, const lb_attn_desc* desc, void* stream);
  * [B*HW, C] (row stride ld), optionally followed by SiLU; fp32 statistics.
  * lb_layernorm: torch.nn.LayerNorm(C, eps) over rows.  Both replace the norm
  * layers inside pipe.unet(...) (diffusers_holder.py:336-344).
+ * The GroupNorm workspace (lb_groupnorm_workspace_bytes) must be ZERO-FILLED once after allocation: it holds
+ * per-batch "last block" counters which every call leaves at zero again; it may be shared by successive calls on
+ * one stream.  Results do not depend on the batch size (row chunking is a function of HW only).
  */
 size_t lb_groupnorm_workspace_bytes(lb_ctx* ctx, int B, int HW, int groups);
 int lb_groupnorm(lb_ctx* ctx, const void* x, int64_t ld, int B, int HW, int C, int groups,

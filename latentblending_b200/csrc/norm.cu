@@ -5,7 +5,8 @@
 // latentblending/diffusers_holder.py:336-344).  HBM/L2-bound: GroupNorm reads x
 // twice (stats pass, apply pass -- the second read is an L2 hit for every SDXL
 // activation) and writes once; LayerNorm is single-read (row kept in registers).
-// Deterministic: fixed-order reductions, no atomics.  fp32 statistics, fp64 final
+// Deterministic and batch-invariant: fixed-order reductions, no floating-point atomics (one integer
+// "last block" counter per batch element finalises the statistics).  fp32 statistics, fp64 final
 // combine; output rounded to fp16 after the affine and again after SiLU, like the
 // reference's two separate torch ops.
 #include "common.cuh"
@@ -17,100 +18,151 @@ constexpr int kMaxC = 2560;
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-// ---- GroupNorm pass 1: per (batch, row-chunk) partial sums per group ------------------
+// ---- GroupNorm ----------------------------------------------------------------------------------
+// Thread layout shared by both passes: a thread owns ONE 16-byte channel vector (8 channels) and walks rows;
+// VP = C/8 vectors per row, RL = 256 / VP row lanes per block (C = 320: 6 lanes x 40 vectors).  All global
+// accesses are 128-bit and coalesced along C, 4 rows in flight per thread, no integer divisions in the loops.
+// The row-chunk grid depends on HW only (not on the batch), so results are bit-identical for any batch size.
+
+// pass 1: per (batch, row-chunk) partial sums per group; the last chunk of a batch element to finish turns the
+// partials into (mean, rstd) per group -- fixed summation order, fp64 combine, no floating-point atomics.
 __global__ void __launch_bounds__(kThreads)
 gn_partial_kernel(const __half* __restrict__ x, long long ld, int C, int HW, int groups, int rows_per_chunk,
-                  float2* __restrict__ partial /*[B][chunks][groups]*/) {
+                  float eps, float2* __restrict__ partial /*[B][chunks][groups]*/,
+                  float2* __restrict__ stats /*[B][groups] (mean, rstd)*/, int* __restrict__ counter /*[B]*/) {
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
     const int row0 = chunk * rows_per_chunk;
     const int row1 = min(HW, row0 + rows_per_chunk);
-    const int pairs = C >> 1;
-    __shared__ float2 s_part[kMaxC / 2];
-    const __half* base = x + ((long long)b * HW) * ld;
-    for (int c2 = threadIdx.x; c2 < pairs; c2 += kThreads) {
-        float s = 0.f, q = 0.f;
-        for (int r = row0; r < row1; ++r) {
-            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(base + (long long)r * ld + 2 * c2));
-            s += v.x + v.y;
-            q = fmaf(v.x, v.x, q);
-            q = fmaf(v.y, v.y, q);
-        }
-        s_part[c2] = make_float2(s, q);
-    }
+    const int VP = C >> 3;
+    const int cpg = C / groups;
+    __shared__ float s_sum[kMaxC], s_sq[kMaxC];
+    __shared__ int s_last;
+    for (int c = threadIdx.x; c < C; c += kThreads) s_sum[c] = s_sq[c] = 0.f;
     __syncthreads();
+    const __half* base = x + ((long long)b * HW) * ld;
+    const int RL = VP <= kThreads ? kThreads / VP : 1;
+    for (int cv0 = 0; cv0 < VP; cv0 += kThreads) {          // one trip unless C > 2048
+        const int cv = cv0 + (VP <= kThreads ? (int)threadIdx.x % VP : (int)threadIdx.x);
+        const int rl = VP <= kThreads ? (int)threadIdx.x / VP : 0;
+        const bool active = cv < VP && rl < RL;
+        float s[8], q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+        if (active) {
+            const __half* col = base + 8 * cv;
+#pragma unroll 4
+            for (int r = row0 + rl; r < row1; r += RL) {
+                const uint4 v = *reinterpret_cast<const uint4*>(col + (long long)r * ld);
+                const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    s[2 * j] += f.x;
+                    s[2 * j + 1] += f.y;
+                    q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+                    q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+                }
+            }
+        }
+        // combine the row lanes in lane order (deterministic); every thread reaches every barrier
+        for (int l = 0; l < RL; ++l) {
+            if (active && rl == l) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s_sum[8 * cv + j] += s[j];
+                    s_sq[8 * cv + j] += q[j];
+                }
+            }
+            __syncthreads();
+        }
+    }
     if (threadIdx.x < groups) {
         const int g = threadIdx.x;
-        const int ppg = pairs / groups;       // channel pairs per group (channels/group is even)
         float s = 0.f, q = 0.f;
-        for (int i = 0; i < ppg; ++i) {
-            const float2 v = s_part[g * ppg + i];
-            s += v.x;
-            q += v.y;
+        for (int i = 0; i < cpg; ++i) {
+            s += s_sum[g * cpg + i];
+            q += s_sq[g * cpg + i];
         }
         partial[((long long)b * chunks + chunk) * groups + g] = make_float2(s, q);
     }
+    // last chunk of this batch element finalises the statistics
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&counter[b], 1) == chunks - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (threadIdx.x < groups) {
+            double s = 0.0, q = 0.0;
+            for (int c = 0; c < chunks; ++c) {
+                const float2 v = __ldcg(&partial[((long long)b * chunks + c) * groups + threadIdx.x]);
+                s += v.x;
+                q += v.y;
+            }
+            const double n = (double)HW * cpg;
+            const double mean = s / n;
+            double var = q / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            stats[(long long)b * groups + threadIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+        }
+        if (threadIdx.x == 0) counter[b] = 0;       // ready for the next launch that shares this workspace
+    }
 }
 
-// ---- GroupNorm pass 2: finish statistics, normalise, affine, optional SiLU ----------------
+// pass 2: normalise, affine, optional SiLU.  Scale / shift of the thread's 8 channels live in registers.
 __global__ void __launch_bounds__(kThreads)
-gn_apply_kernel(const __half* __restrict__ x, long long ld, int C, int HW, int groups, int chunks,
-                const float2* __restrict__ partial, const __half* __restrict__ gamma,
-                const __half* __restrict__ beta, float eps, int do_silu, __half* __restrict__ out, long long ldo,
+gn_apply_kernel(const __half* __restrict__ x, long long ld, int C, int HW, int groups,
+                const float2* __restrict__ stats, const __half* __restrict__ gamma,
+                const __half* __restrict__ beta, int do_silu, __half* __restrict__ out, long long ldo,
                 int rows_per_block) {
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.y;
-    __shared__ float s_mean[64], s_rstd[64];
-    __shared__ float s_scale[kMaxC], s_shift[kMaxC];
+    const int VP = C >> 3;
     const int cpg = C / groups;
-    if (threadIdx.x < groups) {
-        double s = 0.0, q = 0.0;
-        for (int c = 0; c < chunks; ++c) {
-            const float2 v = partial[((long long)b * chunks + c) * groups + threadIdx.x];
-            s += v.x;
-            q += v.y;
-        }
-        const double n = (double)HW * cpg;
-        const double mean = s / n;
-        double var = q / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[threadIdx.x] = (float)mean;
-        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += kThreads) {
-        const int g = c / cpg;
-        const float sc = s_rstd[g] * __half2float(gamma[c]);
-        s_scale[c] = sc;
-        s_shift[c] = __half2float(beta[c]) - s_mean[g] * sc;
-    }
-    __syncthreads();
-    const int vecs = C >> 3;
+    const int RL = VP <= kThreads ? kThreads / VP : 1;
     const int row0 = blockIdx.x * rows_per_block;
     const int row1 = min(HW, row0 + rows_per_block);
-    const long long total = (long long)(row1 - row0) * vecs;
-    for (long long i = threadIdx.x; i < total; i += kThreads) {
-        const int r = row0 + (int)(i / vecs);
-        const int c0 = (int)(i % vecs) * 8;
-        const long long row = (long long)b * HW + r;
-        const uint4 v = *reinterpret_cast<const uint4*>(x + row * ld + c0);
-        const __half2* h = reinterpret_cast<const __half2*>(&v);
-        uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
+    for (int cv0 = 0; cv0 < VP; cv0 += kThreads) {
+        const int cv = cv0 + (VP <= kThreads ? (int)threadIdx.x % VP : (int)threadIdx.x);
+        const int rl = VP <= kThreads ? (int)threadIdx.x / VP : 0;
+        if (cv >= VP || rl >= RL) continue;
+        float sc[8], sh[8];
+        {
+            const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + 8 * cv));
+            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + 8 * cv));
+            const __half* gh = reinterpret_cast<const __half*>(&gv);
+            const __half* bh = reinterpret_cast<const __half*>(&bv);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float2 f = __half22float2(h[j]);
-            float y0 = lb_round_h(fmaf(f.x, s_scale[c0 + 2 * j], s_shift[c0 + 2 * j]));
-            float y1 = lb_round_h(fmaf(f.y, s_scale[c0 + 2 * j + 1], s_shift[c0 + 2 * j + 1]));
-            if (do_silu) {
-                y0 = silu_f(y0);
-                y1 = silu_f(y1);
+            for (int j = 0; j < 8; ++j) {
+                const float2 st = stats[(long long)b * groups + (8 * cv + j) / cpg];     // (mean, rstd)
+                sc[j] = st.y * __half2float(gh[j]);
+                sh[j] = __half2float(bh[j]) - st.x * sc[j];
             }
-            oh[j] = __floats2half2_rn(y0, y1);
         }
-        *reinterpret_cast<uint4*>(out + row * ldo + c0) = o;
+        const __half* col = x + ((long long)b * HW) * ld + 8 * cv;
+        __half* ocol = out + ((long long)b * HW) * ldo + 8 * cv;
+#pragma unroll 4
+        for (int r = row0 + rl; r < row1; r += RL) {
+            const uint4 v = *reinterpret_cast<const uint4*>(col + (long long)r * ld);
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                float y0 = lb_round_h(fmaf(f.x, sc[2 * j], sh[2 * j]));
+                float y1 = lb_round_h(fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]));
+                if (do_silu) {
+                    y0 = silu_f(y0);
+                    y1 = silu_f(y1);
+                }
+                oh[j] = __floats2half2_rn(y0, y1);
+            }
+            *reinterpret_cast<uint4*>(ocol + (long long)r * ldo) = o;
+        }
     }
 }
 
@@ -183,42 +235,52 @@ ln_kernel(const __half* __restrict__ x, long long ld, long long rows, int C, con
 
 }  // namespace
 
-static int gn_chunks(int B, int HW, int sm_count) {
-    int chunks = (2 * sm_count + B - 1) / B;
-    if (chunks > HW) chunks = HW;
-    if (chunks > 256) chunks = 256;
-    if (chunks < 1) chunks = 1;
-    return chunks;
+// row chunks of pass 1: a function of HW only (batch-invariant results)
+static int gn_rows_per_chunk(int HW) {
+    int rpc = (int)lb_ceil_div(HW, 296);
+    if (rpc < 64) rpc = 64;
+    if (rpc > HW) rpc = HW;
+    return rpc;
 }
+static int gn_chunks(int HW) { return (int)lb_ceil_div(HW, gn_rows_per_chunk(HW)); }
 
+// workspace: [kGnMaxBatch] int counters (must start zeroed; every launch leaves them zeroed -- they sit at a fixed
+// offset so one zero-filled buffer can be shared by calls of different shapes) | [B][groups] float2 stats |
+// [B][chunks][groups] float2 partials
+constexpr int kGnMaxBatch = 64;
 extern "C" size_t lb_groupnorm_workspace_bytes(lb_ctx* ctx, int B, int HW, int groups) {
     if (!ctx) return 0;
-    return (size_t)B * gn_chunks(B, HW, ctx->sm_count) * groups * sizeof(float2);
+    return kGnMaxBatch * sizeof(int) + ((size_t)B * gn_chunks(HW) * groups + (size_t)B * groups) * sizeof(float2);
 }
 
 extern "C" int lb_groupnorm(lb_ctx* ctx, const void* x, int64_t ld, int B, int HW, int C, int groups,
                             const void* gamma, const void* beta, float eps, int silu, void* out, int64_t ldo,
                             void* workspace, void* stream) {
     LB_REQUIRE(ctx && x && gamma && beta && out && workspace, "lb_groupnorm: null argument");
-    LB_REQUIRE(groups >= 1 && groups <= 64 && C % groups == 0 && (C / groups) % 2 == 0,
-               "lb_groupnorm: channels per group must be even (C=%d groups=%d)", C, groups);
+    LB_REQUIRE(groups >= 1 && groups <= 64 && C % groups == 0, "lb_groupnorm: C=%d groups=%d", C, groups);
     LB_REQUIRE(C % 8 == 0 && C <= kMaxC, "lb_groupnorm: C must be a multiple of 8 and <= %d (got %d)", kMaxC, C);
-    LB_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && lb_aligned16(x) && lb_aligned16(out), "lb_groupnorm: alignment");
-    const int chunks = gn_chunks(B, HW, ctx->sm_count);
-    const int rpc = (int)lb_ceil_div(HW, chunks);
-    const int used_chunks = (int)lb_ceil_div(HW, rpc);
+    LB_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && lb_aligned16(x) && lb_aligned16(out) && lb_aligned16(gamma) &&
+                   lb_aligned16(beta), "lb_groupnorm: alignment");
+    const int rpc = gn_rows_per_chunk(HW);
+    const int chunks = gn_chunks(HW);
+    LB_REQUIRE(B >= 1 && B <= kGnMaxBatch, "lb_groupnorm: batch %d > %d", B, kGnMaxBatch);
+    int* counter = static_cast<int*>(workspace);
+    float2* stats = reinterpret_cast<float2*>(counter + kGnMaxBatch);
+    float2* partial = stats + (size_t)B * groups;
     cudaStream_t st = lb_stream(stream);
-    lb_launch_pdl(gn_partial_kernel, dim3(used_chunks, B), kThreads, 0, st, (const __half*)x, ld, C, HW, groups, rpc,
-                                                                (float2*)workspace);
+    lb_launch_pdl(gn_partial_kernel, dim3(chunks, B), kThreads, 0, st, (const __half*)x, ld, C, HW, groups, rpc, eps,
+                  partial, stats, counter);
     LB_LAUNCH_CHECK();
-    // apply: ~4 blocks per SM
-    int blocks = (4 * ctx->sm_count + B - 1) / B;
-    if (blocks > HW) blocks = HW;
-    const int rpb = (int)lb_ceil_div(HW, blocks);
+    // apply: ~6 blocks per SM over the whole batch, at least 4 rows per row lane
+    const int VP = C / 8;
+    const int RL = VP <= kThreads ? kThreads / VP : 1;
+    int blocks = (6 * ctx->sm_count + B - 1) / B;
+    int rpb = (int)lb_ceil_div(HW, blocks);
+    if (rpb < 4 * RL) rpb = 4 * RL;
+    if (rpb > HW) rpb = HW;
     blocks = (int)lb_ceil_div(HW, rpb);
-    lb_launch_pdl(gn_apply_kernel, dim3(blocks, B), kThreads, 0, st, (const __half*)x, ld, C, HW, groups, used_chunks,
-                                                          (const float2*)workspace, (const __half*)gamma,
-                                                          (const __half*)beta, eps, silu, (__half*)out, ldo, rpb);
+    lb_launch_pdl(gn_apply_kernel, dim3(blocks, B), kThreads, 0, st, (const __half*)x, ld, C, HW, groups,
+                  (const float2*)stats, (const __half*)gamma, (const __half*)beta, silu, (__half*)out, ldo, rpb);
     LB_LAUNCH_CHECK();
     return 0;
 }

@@ -28,6 +28,18 @@ def _workspace(dev, nbytes):
     return buf
 
 
+_gn_ws_cache = {}
+
+
+def _gn_workspace(dev, nbytes):
+    """lb_groupnorm's workspace holds 'last block' counters that must start at zero (the kernel leaves them zeroed)."""
+    buf = _gn_ws_cache.get(dev)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=f"cuda:{dev}")
+        _gn_ws_cache[dev] = buf
+    return buf
+
+
 def slerp_rows(p0, p1, fract, out=None, fract_rows=None):
     """rows x n whole-row slerp: p0, p1 are [rows, n] (row stride arbitrary, inner
     contiguous).  utils.py:29-71 per row."""
@@ -142,7 +154,7 @@ def groupnorm(x, B, HW, C, groups, gamma, beta, eps, silu, out=None):
     if out is None:
         out = torch.empty((B * HW, C), dtype=torch.float16, device=x.device)
     lib = _cabi.load()
-    ws = _workspace(dev, lib.lb_groupnorm_workspace_bytes(ctx(dev), B, HW, groups))
+    ws = _gn_workspace(dev, lib.lb_groupnorm_workspace_bytes(ctx(dev), B, HW, groups))
     check(lib.lb_groupnorm(ctx(dev), ptr(x), x.stride(0), B, HW, C, groups, ptr(gamma), ptr(beta), float(eps),
                            int(silu), ptr(out), out.stride(0), ptr(ws), stream_ptr()), "lb_groupnorm")
     return out
