@@ -67,6 +67,7 @@ class BlendingEngine():
         self.dt_vae = 0
         self._similarity_fn = similarity_fn
         self.output_device_frames = False     # True: run_transition returns uint8 device frames, no D2H / PIL
+        self.batch_outer_pair = True          # the two outer trajectories share batch-4 UNet forwards (same results)
         self.d2h_bytes = 0                    # bytes copied device->host for returned frames (bench e2e)
         self.lpips = None
         if similarity_fn is None:
@@ -202,8 +203,12 @@ class BlendingEngine():
         rank, world = self._dist()
         if world > 1:
             return self._run_transition_sharded(recycle_img1 and have1, recycle_img2 and have2, rank, world)
-        list_latents1 = self.tree_latents[0] if (recycle_img1 and have1) else self.compute_latents1()
-        list_latents2 = self.tree_latents[-1] if (recycle_img2 and have2) else self.compute_latents2()
+        if (self.batch_outer_pair and hasattr(self.dh, "run_diffusion_sd_xl_multi")
+                and not (recycle_img1 and have1) and not (recycle_img2 and have2)):
+            list_latents1, list_latents2 = self._compute_latents_pair()
+        else:
+            list_latents1 = self.tree_latents[0] if (recycle_img1 and have1) else self.compute_latents1()
+            list_latents2 = self.tree_latents[-1] if (recycle_img2 and have2) else self.compute_latents2()
 
         self.tree_latents = [list_latents1, list_latents2]
         self.tree_fracts = [0.0, 1.0]
@@ -311,16 +316,37 @@ class BlendingEngine():
             return self.dh.latent2image(list_latents1[-1])
         return list_latents1
 
+    def _branch1_crossfeed_coeffs(self):
+        """blending_engine.py:403-408: linspace(power, power*decay, round(N*range)) ++ zeros."""
+        N = self.num_inference_steps
+        idx_mixing_stop = int(round(N * self.branch1_crossfeed_range))
+        mixing_coeffs = list(np.linspace(self.branch1_crossfeed_power,
+                                         self.branch1_crossfeed_power * self.branch1_crossfeed_decay,
+                                         idx_mixing_stop))
+        mixing_coeffs.extend((N - idx_mixing_stop) * [0])
+        return mixing_coeffs
+
+    def _compute_latents_pair(self):
+        """compute_latents1 + compute_latents2 advanced in lockstep through batch-4 UNet forwards (same results:
+        the two trajectories are independent, or -- with branch-1 crossfeed -- trajectory 2 reads step i-1 of
+        trajectory 1, which the lockstep loop has already produced)."""
+        self.dh.set_num_inference_steps(self.num_inference_steps)
+        job1 = dict(text_embeddings=self.get_mixed_conditioning(0)[0], latents_start=self.get_noise(self.seed1))
+        job2 = dict(text_embeddings=self.get_mixed_conditioning(1)[0], latents_start=self.get_noise(self.seed2))
+        if self.branch1_crossfeed_power > 0.0:
+            job2.update(list_latents_mixing=("job", 0), mixing_coeffs=self._branch1_crossfeed_coeffs())
+        ev0, ev1 = self._events()
+        list_latents1, list_latents2 = self.dh.run_diffusion_sd_xl_multi([job1, job2], idx_start=0)
+        self._finish_timing(ev0, ev1, branches=2)
+        self.tree_latents[0] = list_latents1
+        self.tree_latents[-1] = list_latents2
+        return list_latents1, list_latents2
+
     def compute_latents2(self, return_image=False):
         list_conditionings = self.get_mixed_conditioning(1)
         latents_start = self.get_noise(self.seed2)
         if self.branch1_crossfeed_power > 0.0:
-            N = self.num_inference_steps
-            idx_mixing_stop = int(round(N * self.branch1_crossfeed_range))
-            mixing_coeffs = list(np.linspace(self.branch1_crossfeed_power,
-                                             self.branch1_crossfeed_power * self.branch1_crossfeed_decay,
-                                             idx_mixing_stop))
-            mixing_coeffs.extend((N - idx_mixing_stop) * [0])
+            mixing_coeffs = self._branch1_crossfeed_coeffs()
             list_latents2 = self.run_diffusion(list_conditionings, latents_start=latents_start, idx_start=0,
                                                list_latents_mixing=self.tree_latents[0], mixing_coeffs=mixing_coeffs)
         else:
@@ -560,9 +586,9 @@ class BlendingEngine():
             return e0, e1
         return time.time(), None
 
-    def _finish_timing(self, e0, e1):
+    def _finish_timing(self, e0, e1, branches=1):
         if e1 is None:
-            self.dt_unet_step = (time.time() - e0) / self.num_inference_steps
+            self.dt_unet_step = (time.time() - e0) / (self.num_inference_steps * branches)
             return
         e1.record()
-        self._pending_timing = (e0, e1)       # resolved lazily: no host sync inside the transition
+        self._pending_timing = (e0, e1, branches)   # resolved lazily: no host sync inside the transition

@@ -43,6 +43,7 @@ class DiffusersHolder:
         self.unet = UNetB200(pipe.unet_cfg, pipe.unet_state_dict, self.device)
         self.vae = VAEDecoderB200(pipe.vae_state_dict, pipe.vae_channels, pipe.vae_scaling_factor, self.device)
         self.noise_fn = None          # tests: inject the ancestral-step noise, noise_fn(i, shape)
+        self.noise_fn_multi = None    # same for run_diffusion_sd_xl_multi with k > 1: noise_fn_multi(job, i, shape)
         self._cond_key = None
         self.n_unet_calls = 0
 
@@ -117,54 +118,88 @@ class DiffusersHolder:
     @torch.no_grad()
     def run_diffusion_sd_xl(self, text_embeddings, latents_start, idx_start=0, list_latents_mixing=None,
                             mixing_coeffs=0.0, return_image=False):
+        """latentblending/diffusers_holder.py:172-366 for ONE branch (the reference's signature)."""
+        out = self.run_diffusion_sd_xl_multi([dict(text_embeddings=text_embeddings, latents_start=latents_start,
+                                                   list_latents_mixing=list_latents_mixing,
+                                                   mixing_coeffs=mixing_coeffs)], idx_start)[0]
+        if return_image:
+            return self.latent2image(out[-1])
+        return out
+
+    @torch.no_grad()
+    def run_diffusion_sd_xl_multi(self, jobs, idx_start=0):
+        """The denoise loop for k independent branches that share ``idx_start``, advanced in lockstep through ONE
+        UNet forward of batch 2k per step (B200: the 1280-channel levels of a batch-2 SDXL forward are launch- /
+        latency-bound; doubling M is ~17 % cheaper per branch, tools/time_unet_batch.py).  Per branch the arithmetic
+        is exactly run_diffusion_sd_xl's: every kernel on the path is batch-invariant (tests/test_engine_gpu.py).
+
+        jobs: dicts with text_embeddings (4-tuple), latents_start, list_latents_mixing, mixing_coeffs and optionally
+        guidance_scale (default: self.guidance_scale).  ``list_latents_mixing`` may be ``("job", j)``: mix against
+        the trajectory job j is producing in this very call (branch-1 crossfeed reads step i-1, which job j has
+        already written).  Returns one len-N list per job (None for i < idx_start, else [1,4,h,w] fp16 views of that
+        job's trajectory slab)."""
         sched = self.pipe.scheduler
         N = self.num_inference_steps
-        coeffs = self.prepare_mixing(mixing_coeffs, list_latents_mixing)
-        pe, ne, pp, npool = text_embeddings
         sched.set_timesteps(N, device=self.device)
         cfg_on = self.guidance_scale > 1                       # pipe.do_classifier_free_guidance
         hw = self.pipe.default_sample_size * self.pipe.vae_scale_factor   # original/target size, :216-220
         tid = torch.tensor([[hw, hw, 0, 0, hw, hw]], dtype=torch.float16, device=self.device)
-        if cfg_on:
-            ctx = torch.cat([ne, pe], dim=0)
-            text = torch.cat([npool, pp], dim=0)
-            tids = torch.cat([tid, tid], dim=0)
-        else:
-            ctx, text, tids = pe, pp, tid
-        B = 2 if cfg_on else 1
-        _, C, h, w = latents_start.shape
-        plan = self.unet.plan(B, h, w)
-        plan.ctx.copy_(ctx.reshape(plan.ctx.shape))
-        plan.text.copy_(text)
-        plan.tids.copy_(tids)
+        Bj = 2 if cfg_on else 1
+        k = len(jobs)
+        _, C, h, w = jobs[0]["latents_start"].shape
+        ctxs, texts = [], []
+        for job in jobs:
+            pe, ne, pp, npool = job["text_embeddings"]
+            if cfg_on:
+                ctxs += [ne, pe]
+                texts += [npool, pp]
+            else:
+                ctxs.append(pe)
+                texts.append(pp)
+        plan = self.unet.plan(Bj * k, h, w)
+        plan.ctx.copy_(torch.cat(ctxs, dim=0).reshape(plan.ctx.shape))
+        plan.text.copy_(torch.cat(texts, dim=0))
+        plan.tids.copy_(tid.expand(Bj * k, -1))
         plan.prog_ctx.run()                                    # cross-attention K/V: once per conditioning
-        traj = torch.empty((N, C, h, w), dtype=torch.float16, device=self.device)
-        latents = latents_start.clone().contiguous()
-        out = [None] * N
-        n = latents.numel()
+        n = C * h * w
+        outs = [[None] * N for _ in jobs]
+        trajs = [torch.empty((N, C, h, w), dtype=torch.float16, device=self.device) for _ in jobs]
+        coeffs, mixing, guidance, latents = [], [], [], []
+        for job in jobs:
+            m = job.get("list_latents_mixing")
+            if isinstance(m, tuple) and m[0] == "job":
+                m = outs[m[1]]
+            coeffs.append(self.prepare_mixing(job.get("mixing_coeffs", 0.0), m))
+            mixing.append(m)
+            guidance.append(job.get("guidance_scale", self.guidance_scale))
+            latents.append(None)
         for i in range(N):
             if i < idx_start:
                 continue
-            elif i == idx_start:
-                latents = latents_start.clone().contiguous()
-            if i > 0 and coeffs[i] > 0:
-                latents = ops.slerp_rows(latents.view(1, n), list_latents_mixing[i - 1].reshape(1, n),
-                                         float(coeffs[i])).view(1, C, h, w)
             sc = sched.step_scalars[i]
-            ops.scale_model_input(latents, B, sc["divisor"], out=plan.x_in)
+            for j, job in enumerate(jobs):
+                if i == idx_start:
+                    latents[j] = job["latents_start"].clone().contiguous()
+                if i > 0 and coeffs[j][i] > 0:
+                    latents[j] = ops.slerp_rows(latents[j].view(1, n), mixing[j][i - 1].reshape(1, n),
+                                                float(coeffs[j][i])).view(1, C, h, w)
+                ops.scale_model_input(latents[j], Bj, sc["divisor"], out=plan.x_in[j * Bj:(j + 1) * Bj])
             plan.prog_step.run(sc["t"])
             self.n_unet_calls += 1
-            noise = None
-            if sched.ancestral:
-                if self.noise_fn is not None:
-                    noise = self.noise_fn(i, latents.shape).to(device=self.device, dtype=torch.float16).contiguous()
-                else:
-                    noise = torch.randn(latents.shape, device=self.device, dtype=torch.float16)
-            new = traj[i:i + 1]
-            ops.cfg_euler_step(latents, plan.eps, self.guidance_scale, sc["sigma"], sc["dt"], sc["sigma_up"],
-                               noise=noise, out=new)
-            latents = new
-            out[i] = new
-        if return_image:
-            return self.latent2image(latents)
-        return out
+            for j in range(k):
+                noise = None
+                if sched.ancestral:
+                    if k > 1 and self.noise_fn_multi is not None:
+                        noise = self.noise_fn_multi(j, i, latents[j].shape).to(device=self.device,
+                                                                               dtype=torch.float16).contiguous()
+                    elif self.noise_fn is not None:
+                        noise = self.noise_fn(i, latents[j].shape).to(device=self.device,
+                                                                      dtype=torch.float16).contiguous()
+                    else:
+                        noise = torch.randn(latents[j].shape, device=self.device, dtype=torch.float16)
+                new = trajs[j][i:i + 1]
+                ops.cfg_euler_step(latents[j], plan.eps[j * Bj:(j + 1) * Bj], guidance[j], sc["sigma"], sc["dt"],
+                                   sc["sigma_up"], noise=noise, out=new)
+                latents[j] = new
+                outs[j][i] = new
+        return outs

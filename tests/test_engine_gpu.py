@@ -164,6 +164,17 @@ def test_whole_transition_matches_oracle_engine(turbo):
         return f
     oe.dh.run_diffusion_sd_xl = wrap(o_run, oe.dh, "o")
     be.dh.run_diffusion_sd_xl = wrap(b_run, be.dh, "b")
+    # the product runs the two outer trajectories as ONE lockstep batch (run_diffusion_sd_xl_multi with 2 jobs):
+    # job j of that call stands for the oracle's call number c + j
+    m_run = be.dh.run_diffusion_sd_xl_multi
+
+    def multi(jobs, idx_start=0):
+        if len(jobs) > 1:
+            c = calls["b"]
+            calls["b"] += len(jobs)
+            be.dh.noise_fn_multi = lambda j, i, shape: noise_for((c + j, i), shape)
+        return m_run(jobs, idx_start)
+    be.dh.run_diffusion_sd_xl_multi = multi
     for e in (oe, be):
         e.set_dimensions((128, 128))
         e.set_num_inference_steps(N)
@@ -209,3 +220,30 @@ def test_whole_transition_matches_oracle_engine(turbo):
         fp = os.path.join(td, "t.mp4")
         be.write_movie_transition(fp, duration_transition=1, fps=10)
         assert os.path.getsize(fp) > 0
+
+
+@pytest.mark.parametrize("crossfeed", [False, True])
+def test_batched_outer_pair_is_bit_identical_to_sequential(crossfeed):
+    """run_transition computes the two outer trajectories in lockstep through batch-4 UNet forwards
+    (BlendingEngine._compute_latents_pair).  Every kernel on the path is batch-invariant, so the result must equal
+    compute_latents1() followed by compute_latents2() bit for bit -- with and without branch-1 crossfeed."""
+    from latentblending_b200 import BlendingEngine
+    _, pp, _ = _pair(False, seed=5)
+    be = BlendingEngine(pp, run_benchmark=False)
+    be.set_dimensions((256, 128))
+    be.set_num_inference_steps(5)
+    be.set_prompt1("photo of a lake")
+    be.set_prompt2("alien planet")
+    if crossfeed:
+        be.set_branch1_crossfeed(0.7, 0.6, 0.5)
+    be.seed1, be.seed2 = 11, 12
+    seq1 = [t.clone() for t in be.compute_latents1()]
+    seq2 = [t.clone() for t in be.compute_latents2()]
+    bat1, bat2 = be._compute_latents_pair()
+    assert len(bat1) == len(bat2) == 5
+    for i in range(5):
+        assert torch.equal(bat1[i], seq1[i]), f"trajectory 1 step {i}"
+        assert torch.equal(bat2[i], seq2[i]), f"trajectory 2 step {i}"
+    if crossfeed:
+        assert not torch.equal(seq2[-1], be.dh.run_diffusion_sd_xl(be.get_mixed_conditioning(1)[0],
+                                                                  be.get_noise(12))[-1])
