@@ -8,9 +8,13 @@
 //
 // One CTA = 256 query rows (two 128-row halves) of one (batch, head).  Per 128-key tile and half:
 //   S = Q K^T   tcgen05.mma M128 N128 K64, Q/K K-major 128B-swizzled TMA tiles, S in TMEM
-//   softmax     one query row per thread (two warpgroups, one per half, ping-pong against the MMA issuer):
-//               pass 1 row max, pass 2 p = 2^(s*scale - m) -> fp16 P tile in smem (UMMA K-major layout);
-//               TMEM loads are software-pipelined (chunk c+1 in flight while chunk c is processed)
+//   softmax     TWO threads per query row, each owning 64 of the tile's 128 key columns (16 softmax warps: two
+//               groups of 8, one per half, ping-pong against the MMA issuer; the S -> softmax -> P V -> S chain of a
+//               half is serial, so halving the softmax latency shortens every step): pass 1 row max (partners
+//               exchange their partial maxima through smem + a 64-thread named barrier), pass 2
+//               p = 2^(s*scale - m) -> fp16 P tile in smem (UMMA K-major layout).  The 64 S values stay in
+//               registers between the passes: TMEM reads run at 64 B/clk/SM, so reading the fp32 S tile twice
+//               (4096 clk per 256x128 tile) was 4x the tile's MMA time -- the limiter of the earlier versions
 //   O += P V    tcgen05.mma M128 N64 K128 ACCUMULATING IN TMEM, V consumed MN-major from its TMA tile
 // The running maximum is lazy: O (in TMEM) and the row sum are rescaled only when a row's maximum grows by more
 // than 2^8 (then p <= 256, harmless in fp16/fp32); after the first tiles that almost never happens, so the
@@ -40,8 +44,8 @@ constexpr int kD = 64, kBQ = 256, kBKV = 128;   // one CTA: 256 query rows (two 
 constexpr int kTileBytes = 128 * 64 * 2;        // 16 KiB: one Q half / K / V tile
 constexpr int kPBytes = 128 * 128 * 2;          // 32 KiB: one P tile
 constexpr int kKVStages = 2;
-constexpr int kAttnSmem = (2 + 2 * kKVStages) * kTileBytes + 2 * kPBytes + 1024 + 256;
-constexpr int kAttnThreads = 384;               // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 / 8-11 softmax
+constexpr int kAttnSmem = (2 + 2 * kKVStages) * kTileBytes + 2 * kPBytes + 1024 + 256 + 4096 /*row exchange*/;
+constexpr int kAttnThreads = 576;               // warp0 TMEM alloc + TMA, warp1 MMA, warps 2-9 / 10-17 softmax (<= 112 regs)
 constexpr uint32_t kTmemCols = 512;             // S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
 
 // Pipeline (per CTA, one KV tile j = one "step"):
@@ -68,6 +72,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
     uint64_t* p_ready = bars + 11;   // [2]
     uint64_t* o_final = bars + 13;   // [2] last P V of each half has completed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    float* xchg = reinterpret_cast<float*>(bars + 32);     // [parity 2][half 2][colpart 2][128 rows]
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kBQ, head = blockIdx.y, b = blockIdx.z;
@@ -84,12 +89,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
             mbar_init(&v_full[i], 1);
             mbar_init(&v_empty[i], 1);
             mbar_init(&s_full[i], 1);
-            mbar_init(&p_ready[i], 4);
+            mbar_init(&p_ready[i], 8);
             mbar_init(&o_final[i], 1);
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -172,124 +177,150 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
             issue_pv(1, st, j == 0, !more, &v_empty[st]);
             if (more) issue_qk(1, stn, &k_empty[stn]);
         }
-    } else if (warp >= 4) {
-        // ---------------- softmax / output: one query row per thread, two independent halves ----------------
-        const int half = (warp - 4) >> 2;
-        const int quad = warp & 3;
+    } else if (warp >= 2) {
+        // ---------------- softmax / output: two threads per query row, two independent halves ----------------
+        // (any 4 consecutive warps cover the four TMEM lane quadrants: quadrant = warp % 4)
+        const int half = (warp - 2) >> 3;
+        const int colpart = ((warp - 2) >> 2) & 1;     // this thread's 64 key columns: [64*colpart, 64*colpart + 64)
+        const int quad = warp & 3;                      // TMEM lane quadrant of this warp
         const int r = quad * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-        const uint32_t tmem_S = tmem_base + half * 128 + lane_off;
-        const uint32_t tmem_O = tmem_base + 256 + half * 64 + lane_off;
-        uint8_t* sPh = sP + half * kPBytes;
-        float m_run = -INFINITY, l_run = 0.f;     // m_run in the scaled (log2) domain
+        const uint32_t tmem_S = tmem_base + half * 128 + colpart * 64 + lane_off;
+        const uint32_t tmem_O = tmem_base + 256 + half * 64 + colpart * 32 + lane_off;   // its 32 of the 64 O columns
+        uint8_t* prow = sP + half * kPBytes + colpart * 16384 + r * 128;
+        const uint32_t pair_bar = 1 + half * 4 + quad;                      // named barrier of the two partner warps
+        float* x_mine = xchg + (half * 2 + colpart) * 128 + r;
+        const float* x_other = xchg + (half * 2 + (colpart ^ 1)) * 128 + r;
+        const int col0 = colpart * 64;
+        float m_run = -INFINITY, l_run = 0.f;     // m_run in the scaled (log2) domain; l_run: this thread's columns only
         const float sc = p.scale_log2;
+        int kv_valid = kBKV;
+        // row max of this thread's 64 columns (TMEM loads double-buffered)
+        auto max_pass = [&]() -> float {
+            float mx = -INFINITY;
+            uint32_t va[16], vb[16];
+            tmem_ld_32x32b_x16(tmem_S, va);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t (&cur)[16] = (c & 1) ? vb : va;
+                uint32_t (&nxt)[16] = (c & 1) ? va : vb;
+                if (c < 3) tmem_ld_32x32b_x16(tmem_S + (c + 1) * 16, nxt);
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (kv_valid == kBKV || col0 + c * 16 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(cur[i]));
+                if (c < 3) tmem_ld_wait();
+            }
+            return mx;
+        };
+        // p = 2^(s*sc - mref) -> fp16 -> smem (K-major, 128B swizzle: 16B chunk ^= row & 7), row sum and row max in
+        // the SAME sweep over TMEM.  Packed fp32 FMAs; every 4th pair takes the polynomial 2^x so MUFU.EX2
+        // (16/clk/SM) is not the only exp unit.
+        auto exp_pass = [&](float mref, float& psum_out) -> float {
+            float mx = -INFINITY;
+            float2 psum2 = make_float2(0.f, 0.f);
+            const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-mref, -mref);
+            uint32_t va[16], vb[16];
+            tmem_ld_32x32b_x16(tmem_S, va);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t (&cur)[16] = (c & 1) ? vb : va;
+                uint32_t (&nxt)[16] = (c & 1) ? va : vb;
+                if (c < 3) tmem_ld_32x32b_x16(tmem_S + (c + 1) * 16, nxt);
+                if (kv_valid == kBKV) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) mx = fmax3(mx, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (col0 + c * 16 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(cur[i]));
+                }
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    uint4 pk;
+                    __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int col = col0 + c * 16 + g * 8 + 2 * i;
+                        const float2 x2 = ffma2(make_float2(__uint_as_float(cur[g * 8 + 2 * i]),
+                                                            __uint_as_float(cur[g * 8 + 2 * i + 1])), sc2, nm2);
+                        float2 e2;
+                        if (i == 3) {
+                            e2 = ex2_poly2(x2);
+                        } else {
+                            e2.x = ex2_approx(x2.x);
+                            e2.y = ex2_approx(x2.y);
+                        }
+                        if (kv_valid != kBKV) {
+                            if (col >= kv_valid) e2.x = 0.f;
+                            if (col + 1 >= kv_valid) e2.y = 0.f;
+                        }
+                        psum2 = fadd2(psum2, e2);
+                        ph2[i] = __floats2half2_rn(e2.x, e2.y);
+                    }
+                    const int chunk = (c * 2 + g) ^ (r & 7);          // 16-byte chunk inside this row's 128 B
+                    *reinterpret_cast<uint4*>(prow + chunk * 16) = pk;
+                }
+                if (c < 3) tmem_ld_wait();
+            }
+            psum_out = psum2.x + psum2.y;
+            return mx;
+        };
         for (int j = 0; j < nkv; ++j) {
             const uint32_t ph = j & 1;
-            const int kv_valid = min(kBKV, p.Skv - j * kBKV);
+            kv_valid = min(kBKV, p.Skv - j * kBKV);
             mbar_wait(&s_full[half], ph, p.err_flag, 17);
             tc_fence_after();
-            // ---- pass 1: row max (3-input max), TMEM loads double-buffered
-            float mx = -INFINITY;
-            {
-                uint32_t va[32], vb[32];
-                tmem_ld_32x32b_x32(tmem_S, va);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t (&cur)[32] = (c & 1) ? vb : va;
-                    uint32_t (&nxt)[32] = (c & 1) ? va : vb;
-                    if (c < 3) tmem_ld_32x32b_x32(tmem_S + (c + 1) * 32, nxt);
-                    if (kv_valid == kBKV) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(cur[i]));
-                    }
-                    if (c < 3) tmem_ld_wait();
-                }
-            }
-            // ---- lazy maximum: rescale O / l only when some row of this warp outgrew its reference by 2^8
+            // TMEM reads run at 64 B/clk/SM: reading the fp32 S tile twice (max sweep + exp sweep) costs 4096 clk per
+            // 256x128 tile, 4x its MMAs.  So from the second tile on the exps are computed OPTIMISTICALLY against the
+            // running reference maximum in the same sweep that finds the tile's maximum; only if a row outgrew the
+            // reference by more than 2^8 (rare once the reference has settled) is the tile redone after rescaling.
+            float psum = 0.f, mx;
+            if (j == 0) mx = max_pass();
+            else mx = exp_pass(m_run, psum);
+            // partners exchange their partial maxima (double-buffered by step parity)
+            x_mine[ph * 512] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            mx = fmaxf(mx, x_other[ph * 512]);
+            // (both partner warps see identical m_cand / m_run per lane, hence take the same decision)
             const float m_cand = mx * sc;
             if (__any_sync(0xffffffffu, m_cand - m_run > 8.0f)) {      // j == 0: m_run = -inf -> always
                 const float m_new = fmaxf(m_run, m_cand);
                 const float alpha = ex2_approx(m_run - m_new);          // first tile: 2^(-inf) = 0
                 if (j > 0) {
                     // P V(j-1) has completed: S(j) was issued behind it on the in-order tensor pipe
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_O, v);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(tmem_O + c * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        tmem_st_32x32b_x32(tmem_O + c * 32, v);
-                    }
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                    tmem_st_32x32b_x32(tmem_O, v);
                     tmem_st_wait();
                 }
                 l_run *= alpha;
                 m_run = m_new;
+                exp_pass(m_run, psum);                                  // redo this tile against the new reference
             }
-            float2 psum2 = make_float2(0.f, 0.f);
-            const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_run, -m_run);
-            // ---- pass 2: p = 2^(s*sc - m_run) -> fp16 -> smem (K-major, 128B swizzle: 16B chunk ^= row & 7).
-            // Packed fp32 FMAs; every 4th pair takes the polynomial 2^x so MUFU.EX2 (16/clk/SM) is not the only exp unit.
-            {
-                uint32_t va[32], vb[32];
-                tmem_ld_32x32b_x32(tmem_S, va);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t (&cur)[32] = (c & 1) ? vb : va;
-                    uint32_t (&nxt)[32] = (c & 1) ? va : vb;
-                    if (c < 3) tmem_ld_32x32b_x32(tmem_S + (c + 1) * 32, nxt);
-                    uint8_t* prow = sPh + (c >> 1) * 16384 + r * 128;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 pk;
-                        __half2* ph2 = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int col = c * 32 + g * 8 + 2 * i;
-                            const float2 x2 = ffma2(make_float2(__uint_as_float(cur[g * 8 + 2 * i]),
-                                                                __uint_as_float(cur[g * 8 + 2 * i + 1])), sc2, nm2);
-                            float2 e2;
-                            if (i == 3) {
-                                e2 = ex2_poly2(x2);
-                            } else {
-                                e2.x = ex2_approx(x2.x);
-                                e2.y = ex2_approx(x2.y);
-                            }
-                            if (kv_valid != kBKV) {
-                                if (col >= kv_valid) e2.x = 0.f;
-                                if (col + 1 >= kv_valid) e2.y = 0.f;
-                            }
-                            psum2 = fadd2(psum2, e2);
-                            ph2[i] = __floats2half2_rn(e2.x, e2.y);
-                        }
-                        const int chunk = ((c & 1) * 4 + g) ^ (r & 7);
-                        *reinterpret_cast<uint4*>(prow + chunk * 16) = pk;
-                    }
-                    if (c < 3) tmem_ld_wait();
-                }
-            }
-            l_run += psum2.x + psum2.y;
+            l_run += psum;
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[half]);
         }
-        // ---- output: O / l
+        // ---- row sum: partners add their halves (fixed order), then output O / l for this thread's 32 O columns
+        const int fp = (nkv & 1) * 512;           // the exchange buffer the last step did NOT use
+        x_mine[fp] = l_run;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        const float l_tot = colpart ? (x_other[fp] + l_run) : (l_run + x_other[fp]);
         mbar_wait(&o_final[half], 0, p.err_flag, 19);
         tc_fence_after();
         const int q = q0 + half * 128 + r;
-        const float inv = 1.0f / l_run;
-        __half* dst = p.out + ((long long)b * p.Sq + q) * p.ldo + head * kD;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        const float inv = 1.0f / l_tot;
+        __half* dst = p.out + ((long long)b * p.Sq + q) * p.ldo + head * kD + colpart * 32;
+        {
             uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_O + c * 32, v);
+            tmem_ld_32x32b_x32(tmem_O, v);
             tmem_ld_wait();
             if (q < p.Sq) {
 #pragma unroll
@@ -300,7 +331,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
                     for (int i = 0; i < 4; ++i)
                         oh[i] = __floats2half2_rn(__uint_as_float(v[g * 8 + 2 * i]) * inv,
                                                   __uint_as_float(v[g * 8 + 2 * i + 1]) * inv);
-                    *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = o;
+                    *reinterpret_cast<uint4*>(dst + g * 8) = o;
                 }
             }
         }
@@ -308,7 +339,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
