@@ -93,9 +93,25 @@ def dist_env():
 
 
 # ---------------------------------------------------------------------------------------------
+# Analytic FLOPs of one SDXL UNet sample: everything but self-attention scales with the
+# number of latent pixels, self-attention QK^T / PV with its square.
+_UNET_TFLOP_1024 = dict(linear_conv=5.977, self_attn=0.752, cross_attn=0.032)
+
+
+def unet_tflop(latent):
+    r = (latent / 128.0) ** 2
+    u = _UNET_TFLOP_1024
+    return (u["linear_conv"] + u["cross_attn"]) * r + u["self_attn"] * r * r
+
+
+CPU_SAMPLE_LATENT = 64            # the bounded CPU sample runs the oracle at 512x512 px (64x64 latents)
+
+
 def cpu_port_sample(threads=None):
-    """One bounded sample of the CPU oracle at the bench shapes; returns per-op seconds and the
-    frames/s extrapolated with the exact call counts of the workload."""
+    """One bounded sample of the CPU oracle: a full fp32 CFG-batch-2 SDXL UNet forward, a VAE decode and an LPIPS pair
+    at 64x64 latents (512 px) plus a full-size 30-row parental mix; UNet / VAE / LPIPS times are scaled to the bench
+    shape (128x128 latents) by the analytic FLOP ratio and the transition time is extrapolated with the exact call
+    counts of the workload.  A full-size CPU transition would take ~12 h."""
     import torch
     from oracle import mixing
     from oracle.lpips_alex import LPIPSAlex, lpips_distance
@@ -104,6 +120,7 @@ def cpu_port_sample(threads=None):
     if threads:
         torch.set_num_threads(threads)
     cores = torch.get_num_threads()
+    L = CPU_SAMPLE_LATENT
     state = cpu_port_sample.__dict__.setdefault("state", {})
     if "unet" not in state:
         with torch.no_grad():
@@ -111,20 +128,21 @@ def cpu_port_sample(threads=None):
             state["vae"] = VAEDecoder(SDXL_VAE).eval()
             state["lpips"] = LPIPSAlex()
         g = torch.Generator().manual_seed(0)
-        state["x"] = torch.randn(2, 4, 128, 128, generator=g)
+        state["x"] = torch.randn(2, 4, L, L, generator=g)
         state["ctx"] = torch.randn(2, 77, 2048, generator=g) * 0.5
         state["pool"] = torch.randn(2, 1280, generator=g)
-        state["tid"] = torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * 2)
+        state["tid"] = torch.tensor([[8. * L, 8. * L, 0, 0, 8. * L, 8. * L]] * 2)
+        state["lat"] = torch.randn(1, 4, L, L, generator=g).half()
         state["traj"] = [torch.randn(1, 4, 128, 128, generator=g).half() for _ in range(60)]
     s = state
     out = {}
     with torch.no_grad():
         t0 = time.time()
         s["unet"](s["x"], 500.0, s["ctx"], s["pool"], s["tid"])
-        out["t_unet_fwd_b2"] = time.time() - t0
+        out["t_unet_fwd_b2_sample"] = time.time() - t0
         if "t_vae" not in s:
             t0 = time.time()
-            img = latent2image_np(s["vae"], s["traj"][0])
+            img = latent2image_np(s["vae"], s["lat"])
             s["t_vae"] = time.time() - t0
             t0 = time.time()
             mixing.parental_mix(s["traj"][:30], s["traj"][30:], 0.4)
@@ -132,12 +150,22 @@ def cpu_port_sample(threads=None):
             t0 = time.time()
             lpips_distance(s["lpips"], img, img[::-1].copy())
             s["t_lpips"] = time.time() - t0
-    out.update(t_vae=s["t_vae"], t_mix=s["t_mix"], t_lpips=s["t_lpips"])
+    px = (128.0 / L) ** 2
+    out["t_unet_fwd_b2"] = out["t_unet_fwd_b2_sample"] * unet_tflop(128) / unet_tflop(L)
+    out.update(t_vae=s["t_vae"] * px, t_mix=s["t_mix"], t_lpips=s["t_lpips"] * px,
+               t_vae_sample=s["t_vae"], t_lpips_sample=s["t_lpips"])
     total = 198 * out["t_unet_fwd_b2"] + 15 * out["t_vae"] + 13 * out["t_mix"] + 26 * out["t_lpips"]
     out["transition_s_extrapolated"] = total
     out["frames_per_s"] = 15.0 / total
     out["cores"] = cores
     return out
+
+
+CPU_SAMPLE_TEXT = ("bounded sample: 1 fp32 CFG-batch-2 SDXL UNet forward (2.57 B params), 1 VAE decode and 1 LPIPS pair of the "
+                   "CPU oracle at 64x64 latents (512 px) + one full-size 30-row parental mix; UNet time scaled by the "
+                   "analytic FLOP ratio 128^2 vs 64^2 latents (x%.2f), VAE/LPIPS by the pixel ratio (x4); transition "
+                   "time extrapolated with the exact call counts (198 UNet, 15 VAE, 13 mixes, 26 LPIPS)"
+                   % (unet_tflop(128) / unet_tflop(CPU_SAMPLE_LATENT)))
 
 
 def run_reference(args):
@@ -152,9 +180,7 @@ def run_reference(args):
     vals = [cpu_port_sample(threads) for _ in range(max(1, args.steps))]
     fps = sum(v["frames_per_s"] for v in vals) / len(vals)
     tt = sum(v["transition_s_extrapolated"] for v in vals) / len(vals)
-    sample = ("per step: 1 fp32 CFG-batch-2 SDXL UNet forward @128x128 latents timed; VAE decode, 30-row parental "
-              "mix and one LPIPS pair timed once; transition time extrapolated with the exact call counts "
-              "(198 UNet, 15 VAE, 13 mixes, 26 LPIPS)")
+    sample = "per step: " + CPU_SAMPLE_TEXT
     line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=tt * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
                 data="synthetic", config=dict(WORKLOAD), impl="reference",
@@ -253,6 +279,22 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         breakdown[name] = dict(ms=e0.elapsed_time(e1) / reps, launches=n_l)
+    # K1 (crossfeed / parental mix) in its batched form: 2048 rows x 65536 fp16 (805 MB through the kernel, > L2)
+    mp0 = torch.randn(2048, 4 * 128 * 128, device=dev).half()
+    mp1 = torch.randn(2048, 4 * 128 * 128, device=dev).half()
+    mout = torch.empty_like(mp0)
+    for _ in range(3):
+        ops.slerp_rows(mp0, mp1, 0.4, out=mout)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.slerp_rows(mp0, mp1, 0.4, out=mout)
+    e1.record()
+    torch.cuda.synchronize()
+    mix_s = e0.elapsed_time(e1) / 10 * 1e-3
+    mix_gbs = mp0.numel() * 6 / mix_s / 1e9
+    del mp0, mp1, mout
     gemm_tf = work["gemm_flops"] / (breakdown["gemm"]["ms"] * 1e-3) / 1e12
     attn_tf = work["attn_flops"] / (breakdown["attention"]["ms"] * 1e-3) / 1e12
     peak_tf = pk["bf16_tflops_sustained"]
@@ -263,7 +305,14 @@ def run_ours(args):
                     avg_launch_us=breakdown["gemm"]["ms"] * 1e3 / breakdown["gemm"]["launches"],
                     launches_per_unet_forward=breakdown["gemm"]["launches"],
                     unet_forward_breakdown_ms={k: round(v["ms"], 3) for k, v in breakdown.items()},
-                    attention=dict(achieved=attn_tf, frac=attn_tf / peak_tf, flops=work["attn_flops"]))
+                    attention=dict(kernel="attn_tc_kernel (tcgen05 QK^T / PV, head dim 64)", achieved=attn_tf,
+                                   frac=attn_tf / peak_tf, flops=work["attn_flops"],
+                                   note="all 140 attention launches of one UNet forward incl. 70 cross-attention "
+                                        "(77 keys); at d=64 MUFU.EX2 alone caps the tensor pipe at 50 %"),
+                    mix=dict(kernel="slerp_l2_kernel (K1 parental / crossfeed mix, batched 2048 x 65536 fp16)",
+                             bound="hbm", achieved=mix_gbs, peak=pk["hbm_gbs"], unit="GB/s", frac=mix_gbs / pk["hbm_gbs"],
+                             algorithmic_bytes_per_element=6, launch_us=mix_s * 1e6,
+                             traffic="see profiles/ (dram__bytes per launch from ncu)"))
 
     line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=sec / max(1, args.steps) * 1e3, higher_is_better=True, scaling="strong",
@@ -275,8 +324,7 @@ def run_ours(args):
             c = cpu_port_sample(os.cpu_count())
             line["cpu_baseline"] = dict(
                 value=c["frames_per_s"], unit="frames/s", cores=c["cores"], kind="port",
-                sample="1 fp32 CFG-batch-2 SDXL UNet forward @128x128 latents + 1 VAE decode + one 30-row parental mix "
-                       "+ 1 LPIPS pair on the CPU oracle, extrapolated with the exact call counts (198/15/13/26)",
+                sample=CPU_SAMPLE_TEXT,
                 detail={k: round(v, 4) for k, v in c.items() if k.startswith("t_")})
         except Exception as ex:   # the baseline is a reported number, never a reason to lose the bench line
             line["cpu_baseline"] = dict(value=None, unit="frames/s", cores=os.cpu_count(), kind="port",

@@ -28,7 +28,7 @@ ncu)
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_ops.py attn > $O/ncu_attn.log 2>&1; echo "ncu attn exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 12 -o $O/gemm -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_ops.py gemm > $O/ncu_gemm.log 2>&1; echo "ncu gemm exit $?"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:slerp_cluster -s 105 -c 1 -o $O/mix -f \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:slerp_l2 -s 105 -c 1 -o $O/mix -f \
      python tools/bench_mix.py > $O/ncu_mix.log 2>&1; echo "ncu mix exit $?" ;;
 esac
 done
