@@ -312,7 +312,8 @@ def run_ours(args):
                     mix=dict(kernel="slerp_l2_kernel (K1 parental / crossfeed mix, batched 2048 x 65536 fp16)",
                              bound="hbm", achieved=mix_gbs, peak=pk["hbm_gbs"], unit="GB/s", frac=mix_gbs / pk["hbm_gbs"],
                              algorithmic_bytes_per_element=6, launch_us=mix_s * 1e6,
-                             traffic="see profiles/ (dram__bytes per launch from ncu)"))
+                             traffic=790.4e6, traffic_source="ncu dram__bytes_read+write per launch, "
+                             "profiles/r01d_ncu_full_summary.txt (algorithmic: 805.3e6)"))
 
     line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=sec / max(1, args.steps) * 1e3, higher_is_better=True, scaling="strong",

@@ -237,8 +237,8 @@ ln_kernel(const __half* __restrict__ x, long long ld, long long rows, int C, con
 
 // row chunks of pass 1: a function of HW only (batch-invariant results)
 static int gn_rows_per_chunk(int HW) {
-    int rpc = (int)lb_ceil_div(HW, 296);
-    if (rpc < 64) rpc = 64;
+    int rpc = (int)lb_ceil_div(HW, 296);      // at most 296 chunks (2 per SM) per batch element ...
+    if (rpc < 16) rpc = 16;                   // ... of at least 16 rows, so mid-size activations still fill the SMs
     if (rpc > HW) rpc = HW;
     return rpc;
 }
