@@ -1,6 +1,7 @@
 #!/bin/bash
 # One gpurun call: GPU tests, micro-benchmarks, bench line, ncu launch list and ncu full captures.
-# usage (under gpurun): bash tools/gpu_round.sh <tag> [sections...]   sections: tests ops bench launches ncu
+# usage (under gpurun): bash tools/gpu_round.sh <tag> [sections...]
+#   sections: tests smoke optests engine ops mix batch bench parts launches ncu
 set -u
 TAG=${1:-rXX}; shift || true
 SECTIONS=${*:-tests ops bench launches ncu}
@@ -13,6 +14,15 @@ tests)
   ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $O/pytest.log 2>&1; echo "pytest exit $?"; tail -5 $O/pytest.log ;;
 smoke)
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke exit $?"; tail -3 $O/smoke.log ;;
+optests)
+  timeout 600 python -m pytest tests/test_unet_ops_gpu.py tests/test_gemm_gpu.py tests/test_unet_gpu.py tests/test_vae_gpu.py tests/test_mix_step_gpu.py -x -q -m "gpu and not slow" > $O/pytest_ops.log 2>&1; echo "op tests exit $?"; tail -3 $O/pytest_ops.log ;;
+engine)
+  timeout 900 python -m pytest tests/test_engine_gpu.py -x -q -m gpu > $O/pytest_engine.log 2>&1; echo "engine tests exit $?"; tail -3 $O/pytest_engine.log ;;
+mix)
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo tools/ubench_mix.cu -o tools/ubench_mix > $O/ubench_build.log 2>&1
+  timeout 300 tools/ubench_mix > $O/ubench_mix.txt 2>&1; echo "ubench exit $?"; grep -c "mismatching_elements\": 0" $O/ubench_mix.txt; grep "rows\": 1984" $O/ubench_mix.txt ;;
+batch)
+  timeout 300 python tools/time_unet_batch.py > $O/unet_batch.txt 2>&1; cat $O/unet_batch.txt ;;
 ops)
   timeout 300 python tools/bench_ops.py attn gemm > $O/bench_ops.txt 2>&1; cat $O/bench_ops.txt
   timeout 300 python tools/bench_mix.py > $O/bench_mix.txt 2>&1; cat $O/bench_mix.txt ;;
