@@ -45,10 +45,14 @@ constexpr int kABytes = kBM * kBK * 2;  // 16 KiB
 template <int BN> struct Cfg {
     static constexpr int b_bytes = BN * kBK * 2;
     static constexpr int stage_bytes = kABytes + b_bytes;
+    // ring depth is a per-launch parameter (GemmParams::stages): `deep` = as many stages as 227 KB of shared memory
+    // allow (one k-block is 256-320 clk of MMA, a TMA round trip ~1900 clk; measured +4-11 % on the long-K
+    // convolutions), `stages` = the shallower ring the short-K problems were tuned with
     static constexpr int stages = (BN <= 64) ? 8 : (BN <= 128) ? 6 : (BN <= 160) ? 5 : 4;
+    static constexpr int deep = (BN <= 64) ? 8 : (BN <= 128) ? 7 : (BN <= 160) ? 6 : 4;
     static constexpr int tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int smem_bytes(int nst) { return nst * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/; }
     static constexpr int pair_stage_bytes = kABytes + b_bytes / 2;   // bytes ONE CTA of a pair stages per k-block
 };
 
@@ -77,11 +81,12 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + C::stages * kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::stages * C::stage_bytes);
+    const int nst = p.stages;      // ring depth of this launch (Cfg::stages or Cfg::deep)
+    uint8_t* smem_b = smem + nst * kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * C::stage_bytes);
     uint64_t* full = bars;
-    uint64_t* empty = bars + C::stages;
-    uint64_t* tmem_full = bars + 2 * C::stages;
+    uint64_t* empty = bars + nst;
+    uint64_t* tmem_full = bars + 2 * nst;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
         tma_prefetch_desc(&p.tmA[0]);
         tma_prefetch_desc(&p.tmA[1]);
         tma_prefetch_desc(&p.tmB);
-        for (int s = 0; s < C::stages; ++s) {
+        for (int s = 0; s < nst; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
     // that grid is still finishing (the A tiles of the same stages follow after griddepcontrol.wait).
     int early_kb = 0;
     if (CL == 1 && p.static_w && !(p.debug & 1) && tile0 < num_tiles)
-        early_kb = p.total_kb < C::stages ? p.total_kb : C::stages;
+        early_kb = p.total_kb < nst ? p.total_kb : nst;
     if (warp == 0 && early_kb > 0) {
         if (elect_one()) {
             const int n_tile = tile0 / m_groups;
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
                     }
                     }
                     __syncwarp();
-                    if (++stage == C::stages) { stage = 0; phase ^= 1; }
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
                 else umma_commit(&empty[stage]);
                 }
                 __syncwarp();
-                if (++stage == C::stages) { stage = 0; phase ^= 1; }
+                if (++stage == nst) { stage = 0; phase ^= 1; }
             }
             if (elect_one()) {
                 if (CL == 2) umma_commit_2sm(&tmem_full[acc], (uint16_t)0x3);
@@ -419,13 +424,13 @@ template <int BN, int CL> int launch_bn_cl(const GemmPlan& plan, cudaStream_t st
     static bool attr_set = false;
     if (!attr_set) {
         LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg<BN>::smem_bytes));
+                                           Cfg<BN>::smem_bytes(Cfg<BN>::deep)));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)plan.grid);
     cfg.blockDim = dim3(kThreadsGemm);
-    cfg.dynamicSmemBytes = Cfg<BN>::smem_bytes;
+    cfg.dynamicSmemBytes = Cfg<BN>::smem_bytes(plan.p.stages);
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -543,6 +548,14 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
     } else {
         const int tiles = p.tiles_m * p.tiles_n;
         plan->grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    }
+    // ring depth: deep for long-K problems (>= 40 k-blocks: the 3x3 convolutions, FF-out), shallow otherwise
+    {
+        const bool deep = total >= 40 && !getenv("LB_GEMM_SHALLOW");
+        const int bnv = plan->bn;
+        const int shallow_st = (bnv <= 64) ? 8 : (bnv <= 128) ? 6 : (bnv <= 160) ? 5 : 4;
+        const int deep_st = (bnv <= 64) ? 8 : (bnv <= 128) ? 7 : (bnv <= 160) ? 6 : 4;
+        p.stages = deep ? deep_st : shallow_st;
     }
     plan->smem_bytes = 0;
     return 0;
