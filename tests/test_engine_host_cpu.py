@@ -118,3 +118,49 @@ def test_scheduler_tables_known_answers():
     for i, sc in enumerate(t.step_scalars):
         up, down = oa.sigma_up_down(i)
         assert sc["sigma_up"] == float(up.half()) and sc["dt"] == float((down - oa.sigmas[i]).half())
+
+
+def test_batched_outer_pair_wiring_matches_sequential_order():
+    """run_transition hands the two outer trajectories to the holder's lockstep multi-branch loop when it has one
+    (DiffusersHolder.run_diffusion_sd_xl_multi).  With a fake holder whose multi loop simply runs its jobs one after
+    the other (resolving the ("job", j) crossfeed reference), the trajectories and the per-branch call log must equal
+    compute_latents1() followed by compute_latents2() -- with and without branch-1 crossfeed.  (The inner levels need
+    the CUDA parental mix: the whole transition is compared on the GPU in tests/test_engine_gpu.py.)"""
+    import torch
+    from fakes import FakeHolder, fake_similarity
+    from latentblending_b200 import BlendingEngine
+
+    class MultiFake(FakeHolder):
+        def run_diffusion_sd_xl_multi(self, jobs, idx_start=0):
+            outs = []
+            for job in jobs:
+                m = job.get("list_latents_mixing")
+                if isinstance(m, tuple) and m[0] == "job":
+                    m = outs[m[1]]
+                outs.append(self.run_diffusion_sd_xl(job["text_embeddings"], job["latents_start"], idx_start, m,
+                                                     job.get("mixing_coeffs", 0.0)))
+            return outs
+
+    for crossfeed in (False, True):
+        runs = []
+        for batched in (False, True):
+            holder = MultiFake()
+            be = BlendingEngine(None, holder=holder, similarity_fn=fake_similarity, run_benchmark=False)
+            be.set_num_inference_steps(10)
+            be.set_prompt1("a lake")
+            be.set_prompt2("a planet")
+            if crossfeed:
+                be.set_branch1_crossfeed(0.8, 0.6, 0.4)
+            be.seed1, be.seed2 = 420, 421
+            if batched:
+                l1, l2 = be._compute_latents_pair()
+            else:
+                l1, l2 = be.compute_latents1(), be.compute_latents2()
+            assert be.tree_latents[0] is l1 and be.tree_latents[-1] is l2
+            runs.append((l1, l2, holder.calls))
+        (a1, a2, ca), (b1, b2, cb) = runs
+        assert ca == cb and len(ca) == 2
+        if crossfeed:
+            assert isinstance(cb[1]["coeffs"], list) and cb[1]["coeffs"][0] == 0.8 and cb[1]["n_mix_none"] == 0
+        for x0, x1 in zip(a1 + a2, b1 + b2):
+            assert torch.equal(x0, x1)
