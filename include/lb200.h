@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LB_ABI_VERSION 1
+#define LB_ABI_VERSION 2
 
 typedef struct lb_ctx lb_ctx;
 
@@ -78,14 +78,19 @@ int lb_scale_model_input(lb_ctx* ctx, const void* latents_dev, void* out_dev,
  *   eps = u + g*(t-u)                        diffusers_holder.py:347-349
  *   x'  = x + ((x-(x-sigma*eps))/sigma)*dt   diffusers_holder.py:356 (Euler)
  *   x'' = x' + noise*sigma_up                (ancestral only; noise may be NULL)
- * eps_dev holds [2,n] (uncond, text) when use_cfg else [1,n].
+ * eps_dev holds [2,n] (uncond, text) when use_cfg else [1,n]; eps_text_dev (optional) points at the text half when
+ * it is not adjacent to the unconditional one (the two CFG halves computed on two GPUs and exchanged per step).
  * Writes the new latents to out_dev and, if non-NULL, a clone to traj_dev
  * (``list_latents_out.append(latents.clone())``, diffusers_holder.py:359).
+ * scaled_next_dev (optional): the NEXT step's model input, fp16(x'' / next_divisor) replicated scaled_batch times
+ * (the next iteration's diffusers_holder.py:328-330) -- saves the separate lb_scale_model_input launch whenever the
+ * next step has no crossfeed mix in between.
  */
-int lb_cfg_euler_step(lb_ctx* ctx, const void* latents_dev, const void* eps_dev,
+int lb_cfg_euler_step(lb_ctx* ctx, const void* latents_dev, const void* eps_dev, const void* eps_text_dev,
                       const void* noise_dev, void* out_dev, void* traj_dev,
                       int64_t n, int use_cfg, float guidance, float sigma, float dt,
-                      float sigma_up, void* stream);
+                      float sigma_up, void* scaled_next_dev, int scaled_batch, float next_divisor,
+                      void* stream);
 
 /* ---- K7 / K4: tensor-core GEMM and implicit-GEMM convolution ----------------
  * out[M,N] = epilogue( conv_taps(a0)[M, taps*a0_c] | a1[M, a1_c] ) x w[N, K]^T ),
@@ -96,6 +101,13 @@ int lb_cfg_euler_step(lb_ctx* ctx, const void* latents_dev, const void* eps_dev,
  * conv2).  Epilogue mode 0: + bias[n] + bias2[b][n] (time-embedding projection)
  * + res[row][n]; mode 1: GEGLU, N accumulators -> N/2 outputs (weight rows
  * interleaved per 128-column tile: 64 value rows then their 64 gate rows).
+ * LayerNorm fold (ln_stats != NULL; replaces the 210 torch.nn.LayerNorm launches of the transformer blocks): a0 holds
+ * the UN-normalised rows x[M, K]; with w' = w * gamma (per input column), ln_csum[n] = sum_k w'[n,k] and
+ * ln_bias[n] = sum_k beta[k] w[n,k] + bias[n] prepared once on the host,
+ *     LN(x) w^T + bias  ==  rstd_m * (x w'^T - mu_m * ln_csum) + ln_bias,
+ * where (mu_m, rstd_m) come from ln_stats[m][0..ln_parts) = per-row partial (sum, sum of squares) that the GEMM which
+ * PRODUCED x wrote through its stats_out (of its stored fp16 values; stats_parts = 2 * ceil(N / its N tile), reported
+ * by lb_gemm_stats_parts).  Fixed summation order: results do not depend on the batch size.
  * Replaces the cuBLAS / cuDNN calls under pipe.unet(...)
  * (diffusers_holder.py:336-344).  Constraints: a0_c, a1_c multiples of 64;
  * N multiple of 8; W >= 128 or W, (H) powers of two; 16-byte aligned bases.
@@ -111,12 +123,20 @@ typedef struct lb_gemm_desc {
     const void* bias2; int64_t bias2_ld;
     const void* res; int64_t res_ld;
     void* out; int64_t out_ld;
-    int32_t mode;     /* low byte: 0 = linear epilogue, 1 = GEGLU; flags: LB_GEMM_STATIC_W */
+    int32_t mode;     /* low byte: 0 = linear epilogue, 1 = GEGLU; flags: LB_GEMM_STATIC_W, LB_GEMM_RELU */
+    const void* ln_stats; int32_t ln_parts;      /* float2 [M][ln_parts] or NULL */
+    const void* ln_csum; const void* ln_bias;    /* float [N] each */
+    float ln_eps;
+    void* stats_out; int32_t stats_parts;        /* float2 [M][stats_parts] or NULL (linear epilogue only) */
 } lb_gemm_desc;
 /* mode flag: `w` is not written by the kernel that precedes this one on the stream (true for model weights, false
  * when an activation is passed as the B operand): its first tiles may be fetched before the previous kernel ends. */
 #define LB_GEMM_STATIC_W 0x100
+/* mode flag (linear epilogue): out = max(out, 0) -- the AlexNet convolutions of the LPIPS metric */
+#define LB_GEMM_RELU 0x200
 int lb_gemm(lb_ctx* ctx, const lb_gemm_desc* desc, void* stream);
+/* number of per-row partials a GEMM with this desc writes through stats_out (2 per N tile); < 0 on error */
+int lb_gemm_stats_parts(lb_ctx* ctx, const lb_gemm_desc* desc);
 
 /* ---- K8: fused attention, head_dim 64 ----------------------------------------
  * out[b, s, h*64+d] = softmax(Q K^T * scale) V per (batch, head); Q/K/V are
@@ -180,14 +200,44 @@ int lb_im2col_s2(lb_ctx* ctx, const void* x, int64_t ld, int B, int H, int W, in
  * lb_latent_prep: post_quant_conv(latents / scaling_factor) as a per-pixel CxC fp32 matrix (scale folded in).
  * lb_softmax_rows: row softmax of an fp16 matrix (the VAE mid-block single-head attention, head dim 512,
  *   runs as lb_gemm(Q,K) -> lb_softmax_rows -> lb_gemm(P,V^T)).
- * lb_postprocess_u8: (x/2+0.5).clamp(0,1)*255 -> uint8 NHWC (VaeImageProcessor.postprocess).
+ * lb_postprocess_u8: (x/2+0.5).clamp(0,1)*255 -> uint8 NHWC (VaeImageProcessor.postprocess).  nonfinite_count_dev
+ *   (optional, device int) is incremented by the number of NaN/Inf pixels: the decoder runs in fp16 where the reference
+ *   upcasts the stock SDXL VAE to fp32 because it "overflows in float16" (diffusers_holder.py:128-133); an overflow
+ *   anywhere upstream reaches the image as Inf/NaN and is reported instead of silently producing a black frame.
  */
 int lb_latent_prep(lb_ctx* ctx, const void* x_nchw, int B, int C, int64_t hw, const void* w_f32,
                    const void* bias_f32, void* out_nchw, void* stream);
 int lb_softmax_rows(lb_ctx* ctx, const void* x, int64_t ld, int64_t rows, int cols, void* out, int64_t ldo,
                     void* stream);
 int lb_postprocess_u8(lb_ctx* ctx, const void* img_nchw, int B, int C, int64_t hw, void* out_u8_nhwc,
-                      void* stream);
+                      int* nonfinite_count_dev, void* stream);
+
+/* ---- LPIPS-AlexNet branch-placement metric (blending_engine.py:744-758, lpips==0.1.4) ----
+ * The five AlexNet convolutions run on lb_gemm (LB_GEMM_RELU) over patch matrices:
+ * lb_lpips_im2col_u8: conv1's patch matrix [Ho*Wo, out_cols] straight from the uint8 HxWx3 device frame with the
+ *   reference's input arithmetic fused: ((2*u/255 - 1) - shift[c]) / scale[c] (blending_engine.py:750-755 + lpips
+ *   ScalingLayer); column (ky*k + kx)*3 + c, zero columns up to out_cols, zero padding outside the frame.
+ * lb_im2col: generic NHWC fp16 patch matrix [Ho*Wo, k*k*C], column (ky*k + kx)*C + c.
+ * lb_maxpool3s2: MaxPool2d(3, stride 2) on an NHWC map.
+ * lb_lpips_tap: one tap of the distance: mean over pixels of sum_c lin[c] * (a_c/(|a|+1e-10) - b_c/(|b|+1e-10))^2,
+ *   written to (accumulate = 0) or added to (accumulate = 1) the device scalar out_scalar; deterministic.
+ */
+int lb_lpips_im2col_u8(lb_ctx* ctx, const void* frame_u8, int H, int W, int k, int stride, int pad,
+                       const float* shift3, const float* scale3, void* out, int64_t out_cols, void* stream);
+int lb_im2col(lb_ctx* ctx, const void* x, int64_t ld, int H, int W, int C, int k, int stride, int pad, void* out,
+              void* stream);
+int lb_maxpool3s2(lb_ctx* ctx, const void* x, int64_t ld, int H, int W, int C, void* out, int64_t ldo, void* stream);
+size_t lb_lpips_tap_workspace_bytes(lb_ctx* ctx);
+int lb_lpips_tap(lb_ctx* ctx, const void* feat_a, const void* feat_b, int64_t ld, int64_t rows, int C,
+                 const float* lin_w, int accumulate, float* out_scalar, void* workspace, void* stream);
+
+/* ---- frame fill of write_movie_transition (blending_engine.py:684-706, utils.py:105-178) ----
+ * out[t] = uint8( fl32(w0[t] * frames[left[t]]) + fl32(w1[t] * frames[left[t] + 1]) ), t < T, over frames of n bytes
+ * (n % 16 == 0): numpy's float32 blend (w0 = float32(1 - f), w1 = float32(f), no FMA contraction) and its truncating
+ * uint8 cast; w1 == 0 copies the key frame.  left / w0 / w1 are device arrays of length T.
+ */
+int lb_frames_lerp_u8(lb_ctx* ctx, const void* frames_u8, int64_t n, const int* left_idx_dev, const float* w0_dev,
+                      const float* w1_dev, int T, void* out_u8, void* stream);
 
 /* ---- UNet executor ---------------------------------------------------------------
  * A program is a flat list of the ops above over static device buffers (one
@@ -200,7 +250,8 @@ int lb_postprocess_u8(lb_ctx* ctx, const void* img_nchw, int B, int C, int64_t h
 enum {
     LB_OP_GEMM = 1, LB_OP_ATTENTION = 2, LB_OP_GROUPNORM = 3, LB_OP_LAYERNORM = 4, LB_OP_EMBED_INPUTS = 5,
     LB_OP_LINEAR_SMALL = 6, LB_OP_CONV_IN = 7, LB_OP_CONV_OUT = 8, LB_OP_UPSAMPLE2X = 9, LB_OP_IM2COL_S2 = 10,
-    LB_OP_LATENT_PREP = 11, LB_OP_SOFTMAX_ROWS = 12, LB_OP_POSTPROCESS_U8 = 13
+    LB_OP_LATENT_PREP = 11, LB_OP_SOFTMAX_ROWS = 12, LB_OP_POSTPROCESS_U8 = 13,
+    LB_OP_LPIPS_IM2COL_U8 = 14, LB_OP_IM2COL = 15, LB_OP_MAXPOOL3S2 = 16
 };
 typedef struct lb_op {
     int32_t kind;
@@ -218,9 +269,13 @@ typedef struct lb_op {
         struct { const void* x; int64_t ld_x; int32_t B, Cin, H, W; const void* w; const void* bias;
                  int32_t Cout; void* out; int64_t ld_out; } conv;
         struct { const void* x; int64_t ld_x; int32_t B, H, W, C; void* out; int64_t ld_out; } resample;
-        /* LATENT_PREP: x,w,bias,out,B,C,n=h*w; SOFTMAX_ROWS: x,ld_x,out,ld_out,n=rows,C=cols; POSTPROCESS_U8: x,out,B,C,n=h*w */
+        /* LATENT_PREP: x,w,bias,out,B,C,n=h*w; SOFTMAX_ROWS: x,ld_x,out,ld_out,n=rows,C=cols;
+         * POSTPROCESS_U8: x,out,B,C,n=h*w, w = optional device int counter of non-finite pixels */
         struct { const void* x; int64_t ld_x; const void* w; const void* bias; void* out; int64_t ld_out;
                  int64_t n; int32_t B, C; } aux;
+        /* LPIPS_IM2COL_U8 (x = uint8 frame, C = out_cols, f = shift[3], scale[3]); IM2COL; MAXPOOL3S2 (k/stride/pad unused) */
+        struct { const void* x; int64_t ld_x; int32_t H, W, C, k, stride, pad; void* out; int64_t ld_out;
+                 float f[6]; } patch;
     } u;
 } lb_op;
 typedef struct lb_program lb_program;

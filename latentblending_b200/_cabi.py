@@ -27,7 +27,10 @@ class GemmDesc(ctypes.Structure):
                 ("bias2", c_void_p), ("bias2_ld", c_int64),
                 ("res", c_void_p), ("res_ld", c_int64),
                 ("out", c_void_p), ("out_ld", c_int64),
-                ("mode", ctypes.c_int32)]
+                ("mode", ctypes.c_int32),
+                ("ln_stats", c_void_p), ("ln_parts", ctypes.c_int32),
+                ("ln_csum", c_void_p), ("ln_bias", c_void_p), ("ln_eps", c_float),
+                ("stats_out", c_void_p), ("stats_parts", ctypes.c_int32)]
 
 
 class AttnDesc(ctypes.Structure):
@@ -75,9 +78,14 @@ class _AuxOp(ctypes.Structure):
                 ("ld_out", c_int64), ("n", c_int64), ("B", c_int32), ("C", c_int32)]
 
 
+class _PatchOp(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("ld_x", c_int64), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("k", c_int32),
+                ("stride", c_int32), ("pad", c_int32), ("out", c_void_p), ("ld_out", c_int64), ("f", c_float * 6)]
+
+
 class _OpUnion(ctypes.Union):
     _fields_ = [("gemm", GemmDesc), ("attn", AttnDesc), ("norm", _NormOp), ("embed", _EmbedOp), ("lin", _LinOp),
-                ("conv", _ConvOp), ("resample", _ResampleOp), ("aux", _AuxOp)]
+                ("conv", _ConvOp), ("resample", _ResampleOp), ("aux", _AuxOp), ("patch", _PatchOp)]
 
 
 class Op(ctypes.Structure):
@@ -86,8 +94,10 @@ class Op(ctypes.Structure):
 
 
 GEMM_STATIC_W = 0x100     # lb_gemm_desc.mode flag (include/lb200.h: LB_GEMM_STATIC_W)
+GEMM_RELU = 0x200         # LB_GEMM_RELU
 (OP_GEMM, OP_ATTENTION, OP_GROUPNORM, OP_LAYERNORM, OP_EMBED_INPUTS, OP_LINEAR_SMALL, OP_CONV_IN, OP_CONV_OUT,
- OP_UPSAMPLE2X, OP_IM2COL_S2, OP_LATENT_PREP, OP_SOFTMAX_ROWS, OP_POSTPROCESS_U8) = range(1, 14)
+ OP_UPSAMPLE2X, OP_IM2COL_S2, OP_LATENT_PREP, OP_SOFTMAX_ROWS, OP_POSTPROCESS_U8, OP_LPIPS_IM2COL_U8, OP_IM2COL,
+ OP_MAXPOOL3S2) = range(1, 17)
 
 
 # name -> (restype, argtypes); mirrors include/lb200.h one to one
@@ -102,9 +112,10 @@ SIGNATURES = {
                               c_int, c_double, c_void_p, c_void_p, c_void_p]),
     "lb_lerp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p]),
     "lb_scale_model_input": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
-    "lb_cfg_euler_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-                                  c_float, c_float, c_float, c_float, c_void_p]),
+    "lb_cfg_euler_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                  c_float, c_float, c_float, c_float, c_void_p, c_int, c_float, c_void_p]),
     "lb_gemm": (c_int, [c_void_p, ctypes.POINTER(GemmDesc), c_void_p]),
+    "lb_gemm_stats_parts": (c_int, [c_void_p, ctypes.POINTER(GemmDesc)]),
     "lb_ctx_error_flag": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "lb_program_create": (c_int, [c_void_p, ctypes.POINTER(Op), c_int64, ctypes.POINTER(c_void_p)]),
     "lb_program_run": (c_int, [c_void_p, c_float, c_void_p]),
@@ -130,7 +141,16 @@ SIGNATURES = {
     "lb_im2col_s2": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "lb_latent_prep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lb_softmax_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
-    "lb_postprocess_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),
+    "lb_postprocess_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "lb_lpips_im2col_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float),
+                                   ctypes.POINTER(c_float), c_void_p, c_int64, c_void_p]),
+    "lb_im2col": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "lb_maxpool3s2": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "lb_lpips_tap_workspace_bytes": (c_size_t, [c_void_p]),
+    "lb_lpips_tap": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p,
+                             c_void_p, c_void_p]),
+    "lb_frames_lerp_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                  c_void_p]),
 }
 
 _lib = None
@@ -159,7 +179,7 @@ def load():
             fn = getattr(lib, name)       # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.lb_abi_version() != 1:
+        if lib.lb_abi_version() != 2:
             raise LB200Error("liblb200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -26,7 +26,7 @@ from PIL import Image
 
 from . import ops
 from .diffusers_holder import DiffusersHolder
-from .next_rows import TorchLPIPSAlex, lpips_random_state_dict
+from .lpips import LPIPSAlexB200, lpips_random_state_dict
 from .utils import add_frames_linear_interp, interpolate_linear
 
 warnings.filterwarnings('ignore')
@@ -70,9 +70,18 @@ class BlendingEngine():
         self.batch_outer_pair = True          # the two outer trajectories share batch-4 UNet forwards (same results)
         self.d2h_bytes = 0                    # bytes copied device->host for returned frames (bench e2e)
         self.lpips = None
+        self._pending_timing = None
         if similarity_fn is None:
-            sd = getattr(pipe, "lpips_state_dict", None) or lpips_random_state_dict(2, self.device)
-            self.lpips = TorchLPIPSAlex(sd, self.device)
+            sd = getattr(pipe, "lpips_state_dict", None)
+            if sd is None:
+                # Random AlexNet weights only RANK gaps of a synthetic pipe; with real UNet / VAE weights they would
+                # silently steer branch placement away from the reference's LPIPS (blending_engine.py:74-76).
+                if not getattr(pipe, "is_synthetic", False):
+                    raise ValueError(
+                        "pipe has no lpips_state_dict: export the lpips==0.1.4 AlexNet weights (see INTEGRATION.md, "
+                        "'LPIPS weights') and pass them as pipe.lpips_state_dict, or supply similarity_fn=...")
+                sd = lpips_random_state_dict(2, self.device)
+            self.lpips = LPIPSAlexB200(sd, self.device)
         self.set_prompt1("")
         self.set_prompt2("")
         self.set_branch1_crossfeed()
@@ -168,6 +177,7 @@ class BlendingEngine():
         self.dh.set_num_inference_steps(num_inference_steps)
 
     def set_branching(self, depth_strength=None, t_compute_max_allowed=None, nmb_max_branches=None):
+        self._resolve_timing()
         if self.dh.is_sdxl_turbo:
             assert t_compute_max_allowed is None, "time-based branching not supported for SDXL Turbo"
             idx_inject = int(round(self.num_inference_steps * depth_strength)) if depth_strength is not None else 2
@@ -226,6 +236,11 @@ class BlendingEngine():
                 self.set_guidance_mid_dampening(fract_mixing)
                 list_latents = self.compute_latents_mix(fract_mixing, b_parent1, b_parent2, idx_injection)
                 self.insert_into_tree(fract_mixing, idx_injection, list_latents)
+        return self._finish_transition()
+
+    def _finish_transition(self):
+        if hasattr(self.dh, "check_decode_overflow"):
+            self.dh.check_decode_overflow()       # fp16 VAE: raise instead of returning black / garbage frames
         if self.output_device_frames:
             self.tree_final_imgs = list(self._tree_frames)
         else:
@@ -265,45 +280,66 @@ class BlendingEngine():
         dist.broadcast_object_list(seeds, src=0)            # 'randomize' draws must agree across ranks
         self.seed1, self.seed2 = seeds
         crossfed = self.branch1_crossfeed_power > 0.0
+        cfg_on = self.dh.guidance_scale > 1
+        sharder = getattr(self, "_sharder", None)
+        if sharder is None or sharder.world != world:
+            sharder = self._sharder = LevelSharder(rank, world, device=self.device, cfg_pairs=cfg_on)
+        sharder.cfg_pairs = cfg_on and world >= 2
+        sharder.stats = dict(rounds=0, computed=0, used=0, paired_rounds=0)
+        # ---- outer trajectories.  Owners: trajectory 1 -> rank 0, trajectory 2 -> rank 1 (both on rank 0 in one
+        # lockstep batch when branch-1 crossfeed couples them).  From 4 ranks up (CFG on) each owner becomes a PAIR:
+        # ranks (0,1) / (2,3) split the CFG halves of their trajectory (batch-1 forwards + one eps exchange per step).
+        # On 2-3 ranks a pair is used when only one trajectory has to be computed (the other is recycled) or when
+        # crossfeed forces both onto the same ranks anyway.
+        n_outer = int(not reuse1) + int(not reuse2)
+        paired = cfg_on and (world >= 4 or (world >= 2 and n_outer >= 1 and (n_outer == 1 or crossfed)))
+        split = dict(group=sharder.pair_group(), half=rank % 2) if paired else None
         t1 = self.tree_latents[0] if reuse1 else None
         t2 = self.tree_latents[-1] if reuse2 else None
+        own1 = (0, 1) if paired else (0,)
+        # crossfeed: trajectory 2 reads trajectory 1, so it runs where trajectory 1 lives
+        own2 = own1 if (crossfed or (paired and world < 4)) else ((2, 3) if paired else (1,))
+        mine1 = mine2 = None
+        self.dh.cfg_split = split
+        try:
+            if crossfed and not reuse1 and not reuse2:
+                if rank in own1:
+                    mine1, mine2 = self._compute_latents_pair()          # lockstep: step i of 2 reads step i-1 of 1
+            else:
+                if not reuse1 and rank in own1:
+                    mine1 = self.compute_latents1()
+                if not reuse2 and rank in own2:
+                    mine2 = self.compute_latents2()                       # crossfed here implies reuse1: every rank has t1
+        finally:
+            self.dh.cfg_split = None
         if not reuse1:
-            mine = self.compute_latents1() if rank == 0 else None
-            if crossfed or reuse2:
-                t1 = self._bcast_trajectory(mine, 0)        # branch 2 reads branch 1 step by step
-                self.tree_latents[0] = t1
+            t1 = self._bcast_trajectory(mine1, own1[0])
         if not reuse2:
-            owner = 0 if crossfed else 1
-            mine2 = self.compute_latents2() if rank == owner else None
-            if t1 is None:
-                t1 = self._bcast_trajectory(mine, 0)
-            t2 = self._bcast_trajectory(mine2, owner)
-        elif t1 is None:
-            t1 = self._bcast_trajectory(mine, 0)
+            t2 = self._bcast_trajectory(mine2, own2[0])
         self.tree_latents = [t1, t2]
         self.tree_fracts = [0.0, 1.0]
         self._tree_frames = [self._decode_frame(t1[-1]), self._decode_frame(t2[-1])]
         self.tree_idx_injection = [0, 0]
         self.tree_similarities = [None]
-        sharder = LevelSharder(rank, world, device=self.device)
 
-        def compute(fract, p1, p2, idx_injection):
+        def compute(fract, p1, p2, idx_injection, cfg_split=None):
             self.set_guidance_mid_dampening(fract)
-            traj = self.compute_latents_mix(fract, p1, p2, idx_injection)
+            self.dh.cfg_split = cfg_split
+            try:
+                traj = self.compute_latents_mix(fract, p1, p2, idx_injection)
+            finally:
+                self.dh.cfg_split = None
             return traj, self._decode_frame(traj[-1])
 
-        def similarity(fa, fb):
-            return self.get_lpips_similarity(fa, fb) if rank == 0 else 0.0
-
         for s_idx in range(len(self.list_idx_injection)):
+            # every rank evaluates the (deterministic) similarities on the replicated frames and replays
+            # set_guidance_mid_dampening for every INSERTED branch in insertion order, so all ranks leave the
+            # transition with the sequential path's tree AND guidance state (the latter steers the next transition's
+            # outer trajectories and the do_cfg decision of set_prompt, blending_engine.py:147,164)
             sharder.run_level(self, int(self.list_idx_injection[s_idx]), int(self.list_nmb_stems[s_idx]), compute,
-                              similarity, N)
-        self.shard_stats = sharder.stats
-        if self.output_device_frames:
-            self.tree_final_imgs = list(self._tree_frames)
-        else:
-            self.tree_final_imgs = [self._frame_to_pil(f) for f in self._tree_frames]
-        return self.tree_final_imgs
+                              self.get_lpips_similarity, N, on_insert=self.set_guidance_mid_dampening)
+        self.shard_stats = dict(sharder.stats)
+        return self._finish_transition()
 
     def compute_latents1(self, return_image=False):
         list_conditionings = self.get_mixed_conditioning(0)
@@ -407,6 +443,7 @@ class BlendingEngine():
                                   list_latents_mixing=list_latents_parental_mix, mixing_coeffs=mixing_coeffs)
 
     def get_time_based_branching(self, depth_strength, t_compute_max_allowed=None, nmb_max_branches=None):
+        self._resolve_timing()
         N = self.num_inference_steps
         idx_injection_base = int(np.floor(N * depth_strength))
         steps = int(np.ceil(N / 10))
@@ -503,8 +540,7 @@ class BlendingEngine():
         """Fill up to duration*fps frames by linear interpolation and encode with OpenCV
         (the reference uses lunar_tools.MovieSaver/ffmpeg, blending_engine.py:684-706)."""
         import cv2
-        frames = add_frames_linear_interp([np.asarray(im) for im in self.tree_final_imgs], fps_target=fps,
-                                          duration_target=duration_transition)
+        frames = self.get_movie_frames(duration_transition, fps)
         if os.path.isfile(fp_movie):
             os.remove(fp_movie)
         h, w = self.dh.height_img, self.dh.width_img
@@ -515,6 +551,26 @@ class BlendingEngine():
                 f = cv2.resize(f, (w, h))
             vw.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
         vw.release()
+
+    def get_movie_frames(self, duration_transition, fps=30, seed=None):
+        """The duration*fps frames of the transition movie as one uint8 array [T,H,W,3]: the tree frames plus the
+        linear fill of utils.py:105-178 (add_frames_linear_interp), blended ON THE DEVICE by lb_frames_lerp_u8 from
+        the device-resident key frames -- one launch, one device->host copy (the reference blends T float32 images
+        on the CPU).  With a foreign holder whose frames are host images the same plan runs through the numpy
+        version (utils.add_frames_linear_interp), which is the reference's own algorithm."""
+        from .utils import plan_frame_fill
+        keys = getattr(self, "_tree_frames", None)
+        if not keys or not all(torch.is_tensor(f) and f.is_cuda for f in keys):
+            return np.stack([np.asarray(f) for f in add_frames_linear_interp(
+                [np.asarray(im) for im in self.tree_final_imgs], fps_target=fps, duration_target=duration_transition,
+                seed=seed)], 0)
+        left, w0, w1 = plan_frame_fill(len(keys), fps * duration_transition, seed=seed)
+        stack = torch.stack(keys, 0).contiguous()
+        F_, H, W, C = stack.shape
+        dev = stack.device
+        out = ops.frames_lerp_u8(stack.view(F_, H * W * C), torch.from_numpy(left).to(dev),
+                                 torch.from_numpy(w0).to(dev), torch.from_numpy(w1).to(dev))
+        return out.view(-1, H, W, C).cpu().numpy()
 
     def get_state_dict(self):
         state_dict = {}
@@ -591,4 +647,16 @@ class BlendingEngine():
             self.dt_unet_step = (time.time() - e0) / (self.num_inference_steps * branches)
             return
         e1.record()
-        self._pending_timing = (e0, e1, branches)   # resolved lazily: no host sync inside the transition
+        # resolved lazily by set_branching / get_time_based_branching: no host sync inside the transition
+        self._pending_timing = (e0, e1, branches, self.num_inference_steps)
+
+    def _resolve_timing(self):
+        """dt_unet_step tracks the last outer trajectory like blending_engine.py:379-386 (time per UNet step of ONE
+        branch), from CUDA events recorded around it."""
+        pend = getattr(self, "_pending_timing", None)
+        if pend is None:
+            return
+        self._pending_timing = None
+        e0, e1, branches, n = pend
+        e1.synchronize()
+        self.dt_unet_step = e0.elapsed_time(e1) / 1e3 / (n * branches)

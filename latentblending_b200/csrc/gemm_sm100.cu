@@ -68,6 +68,29 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     }
 }
 
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// (mu, rstd) of one row of the LayerNorm-folded A operand from the producer's per-row partial sums (fixed order)
+__device__ __forceinline__ void ln_row_stats(const GemmParams& p, long long row, bool ok, float& mu, float& rstd) {
+    mu = 0.f;
+    rstd = 1.f;
+    if (!ok) return;
+    float s = 0.f, q = 0.f;
+    const float2* st = p.ln_stats + row * p.ln_parts;
+    for (int i = 0; i < p.ln_parts; ++i) {
+        const float2 v = __ldcg(st + i);
+        s += v.x;
+        q += v.y;
+    }
+    mu = s * p.ln_inv_k;
+    double var = (double)q * (double)p.ln_inv_k - (double)mu * (double)mu;
+    if (var < 0.0) var = 0.0;
+    rstd = rsqrtf((float)var + p.ln_eps);
+}
+
 // CL = 2 (cta_group::2): a CTA PAIR owns a 256 x BN tile -- two vertically adjacent 128-row M tiles of one N tile.
 // Each CTA stages its own A tile and HALF of the weight tile; the leader issues tcgen05.mma.cta_group::2 (M = 256),
 // each SM's tensor core accumulates its 128 rows in its own TMEM and the weight halves are shared across the pair,
@@ -251,6 +274,9 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
                     }
                 };
                 if (c_begin < c_end) load_res(c_begin, rnext);
+                float ln_mu = 0.f, ln_rstd = 1.f;
+                if (p.ln_stats) ln_row_stats(p, row, row_ok, ln_mu, ln_rstd);   // overlaps the MMAs of this tile
+                float st_sum = 0.f, st_sq = 0.f;
                 mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 4);
                 tc_fence_after();
 #pragma unroll
@@ -274,7 +300,14 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) acc8[j] = __uint_as_float(v[g * 8 + j]);
                                     float t8[8];
-                                    if (p.bias) {
+                                    if (p.ln_stats) {
+                                        float c8[8];
+                                        load8f(p.ln_csum + n, c8);
+                                        load8f(p.ln_bias + n, t8);
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j)
+                                            acc8[j] = fmaf(ln_rstd, acc8[j] - ln_mu * c8[j], t8[j]);
+                                    } else if (p.bias) {
                                         unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + n)), t8);
 #pragma unroll
                                         for (int j = 0; j < 8; ++j) acc8[j] += t8[j];
@@ -289,16 +322,30 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
                                         for (int j = 0; j < 8; ++j) acc8[j] += t8[j];
                                     }
+                                    if (p.relu) {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) acc8[j] = fmaxf(acc8[j], 0.f);
+                                    }
                                     uint4 o;
                                     __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
                                     for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc8[2 * j], acc8[2 * j + 1]);
                                     *reinterpret_cast<uint4*>(p.out + row * p.ldo + n) = o;
+                                    if (p.stats_out) {       // statistics of the STORED (fp16-rounded) values
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            const float2 f = __half22float2(oh[j]);
+                                            st_sum += f.x + f.y;
+                                            st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
+                                        }
+                                    }
                                 }
                             }
                         }
                     }
                 }
+                if (p.stats_out && row_ok)
+                    p.stats_out[row * (2 * p.tiles_n) + 2 * n_tile + part] = make_float2(st_sum, st_sq);
             } else {
                 // GEGLU: tile columns [0,BN/2) are "value", [BN/2,BN) the matching "gate" (weights are
                 // row-interleaved per tile on the host); out = (v+bv) * gelu(g+bg), BN/2 outputs per tile.
@@ -308,6 +355,8 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
                 const int c_begin = part ? NCH0 : 0, c_end = part ? NCH : NCH0;
                 const int o_base = n_tile * HN;        // output column base
                 const int a_base = n_tile * BN;        // accumulator (bias) column base
+                float ln_mu = 0.f, ln_rstd = 1.f;
+                if (p.ln_stats) ln_row_stats(p, row, row_ok, ln_mu, ln_rstd);
                 mbar_wait(&tmem_full[acc], acc_phase, p.err_flag, 4);
                 tc_fence_after();
 #pragma unroll 1
@@ -321,7 +370,18 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
                         for (int g = 0; g < 4; ++g) {
                             float bv[8], bg[8];
                             const int jn = c * 32 + g * 8;
-                            if (p.bias) {
+                            if (p.ln_stats) {
+                                float cv[8], cg[8];
+                                load8f(p.ln_csum + a_base + jn, cv);
+                                load8f(p.ln_csum + a_base + HN + jn, cg);
+                                load8f(p.ln_bias + a_base + jn, bv);
+                                load8f(p.ln_bias + a_base + HN + jn, bg);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    vv[g * 8 + j] = __float_as_uint(ln_rstd * (__uint_as_float(vv[g * 8 + j]) - ln_mu * cv[j]));
+                                    vg[g * 8 + j] = __float_as_uint(ln_rstd * (__uint_as_float(vg[g * 8 + j]) - ln_mu * cg[j]));
+                                }
+                            } else if (p.bias) {
                                 unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + a_base + jn)), bv);
                                 unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + a_base + HN + jn)), bg);
                             } else {
@@ -535,6 +595,27 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
     p.ldr = d.res_ld;
     p.err_flag = lb_err_flag(ctx);
     p.debug = getenv("LB_GEMM_DEBUG") ? atoi(getenv("LB_GEMM_DEBUG")) : 0;
+    p.relu = (d.mode & LB_GEMM_RELU) ? 1 : 0;
+    LB_REQUIRE(!p.relu || p.mode == 0, "gemm: LB_GEMM_RELU needs the linear epilogue");
+    if (d.ln_stats) {
+        LB_REQUIRE(d.ln_csum && d.ln_bias && d.ln_parts >= 1 && d.ln_parts <= 64, "gemm: LayerNorm fold needs ln_csum, "
+                   "ln_bias and 1 <= ln_parts <= 64");
+        LB_REQUIRE(d.taps == 1 && !d.a1 && !d.res && !d.bias2 && !d.bias, "gemm: LayerNorm fold applies to a plain linear "
+                   "(its bias is part of ln_bias)");
+        LB_REQUIRE(lb_aligned16(d.ln_csum) && lb_aligned16(d.ln_bias) && lb_aligned16(d.ln_stats), "gemm: ln_* alignment");
+        p.ln_stats = static_cast<const float2*>(d.ln_stats);
+        p.ln_parts = d.ln_parts;
+        p.ln_csum = static_cast<const float*>(d.ln_csum);
+        p.ln_bias = static_cast<const float*>(d.ln_bias);
+        p.ln_inv_k = 1.0f / (float)d.a0_c;
+        p.ln_eps = d.ln_eps;
+    }
+    if (d.stats_out) {
+        LB_REQUIRE(p.mode == 0, "gemm: stats_out needs the linear epilogue");
+        LB_REQUIRE(d.stats_parts == 2 * p.tiles_n, "gemm: stats_parts must be 2 * ceil(N / %d) = %d (got %d)", bn,
+                   2 * p.tiles_n, d.stats_parts);
+        p.stats_out = static_cast<float2*>(d.stats_out);
+    }
     // CTA pairs (cta_group::2, M = 256) whenever there are at least two M tiles
     // (measured: the pair wins ~3 % on long-K multi-wave problems -- the big convolutions -- and loses up to 15 %
     //  on short-K / single-wave ones, where its cluster launch + sync overhead dominates)
@@ -570,6 +651,15 @@ int gemm_plan_launch(const GemmPlan& plan, cudaStream_t st) {
     }
     lb_set_error("gemm: unsupported N tile %d", plan.bn);
     return 2;
+}
+
+extern "C" int lb_gemm_stats_parts(lb_ctx* ctx, const lb_gemm_desc* desc) {
+    if (!ctx || !desc) return -1;
+    GemmDesc d = *reinterpret_cast<const GemmDesc*>(desc);
+    d.stats_out = nullptr;
+    GemmPlan plan;
+    if (gemm_plan_build(ctx, d, &plan)) return -1;
+    return 2 * plan.p.tiles_n;
 }
 
 extern "C" int lb_gemm(lb_ctx* ctx, const lb_gemm_desc* desc, void* stream) {

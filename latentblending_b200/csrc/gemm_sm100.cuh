@@ -14,7 +14,11 @@ struct GemmDesc {
     const void* bias2; int64_t bias2_ld;
     const void* res; int64_t res_ld;
     void* out; int64_t out_ld;
-    int32_t mode;   // low byte: 0 linear epilogue, 1 GEGLU (N accumulators -> N/2 outputs); | LB_GEMM_STATIC_W
+    int32_t mode;   // low byte: 0 linear epilogue, 1 GEGLU (N accumulators -> N/2 outputs); | LB_GEMM_STATIC_W | LB_GEMM_RELU
+    // LayerNorm folded into this GEMM (see include/lb200.h)
+    const void* ln_stats; int32_t ln_parts;
+    const void* ln_csum; const void* ln_bias; float ln_eps;
+    void* stats_out; int32_t stats_parts;
 };
 
 constexpr int kGemmMaxSegs = 12;
@@ -39,6 +43,12 @@ struct alignas(64) GemmParams {
     const __half* res; long long ldr;
     int* err_flag;
     int debug;     // profiling knobs (LB_GEMM_DEBUG): 1 = skip TMA issue, 2 = skip MMA issue
+    int relu;      // mode 0: out = max(out, 0) (LB_GEMM_RELU)
+    // LayerNorm fold: A holds the UN-normalised rows x; out = rstd*(acc - mu*csum[n]) + lnb[n] with (mu, rstd) from the
+    // per-row partial sums the producing GEMM wrote (ln_stats[row][ln_parts] = (sum, sum of squares))
+    const float2* ln_stats; int ln_parts; float ln_inv_k, ln_eps;
+    const float* ln_csum; const float* ln_bias;
+    float2* stats_out;     // [M][2*tiles_n]: (sum, sum of squares) of this launch's fp16 outputs per row and column part
 };
 
 struct GemmPlan {

@@ -443,18 +443,28 @@ softmax_rows_kernel(const __half* __restrict__ x, long long ld, int cols, __half
     }
 }
 
-// VaeImageProcessor.postprocess: NCHW fp16 image -> uint8 NHWC, (x/2+0.5).clamp(0,1)*255 rounded half-to-even
+// VaeImageProcessor.postprocess: NCHW fp16 image -> uint8 NHWC, (x/2+0.5).clamp(0,1)*255 rounded half-to-even.
+// `nonfinite` (optional) counts NaN/Inf pixels: the decoder runs in fp16 where the reference upcasts the stock SDXL VAE
+// to fp32 ("overflows in float16", diffusers_holder.py:128); an overflow anywhere upstream reaches the image as Inf/NaN.
 __global__ void __launch_bounds__(kThreads)
-postprocess_u8_kernel(const __half* __restrict__ img, int B, int C, long long hw, uint8_t* __restrict__ out) {
+postprocess_u8_kernel(const __half* __restrict__ img, int B, int C, long long hw, uint8_t* __restrict__ out,
+                      int* __restrict__ nonfinite) {
     pdl_launch_dependents();
     pdl_wait();
     const long long total = (long long)B * hw * C;
+    int bad = 0;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
         const int c = (int)(i % C);
         const long long p = (i / C) % hw, b = i / (C * hw);
-        float v = __half2float(img[(b * C + c) * hw + p]) / 2.0f + 0.5f;
+        const float raw = __half2float(img[(b * C + c) * hw + p]);
+        bad += !isfinite(raw);
+        float v = raw / 2.0f + 0.5f;
         v = fminf(fmaxf(v, 0.f), 1.f);
         out[i] = (uint8_t)__float2int_rn(v * 255.0f);
+    }
+    if (nonfinite != nullptr && __any_sync(0xffffffffu, bad != 0)) {
+        bad = __reduce_add_sync(0xffffffffu, bad);
+        if ((threadIdx.x & 31) == 0) atomicAdd(nonfinite, bad);
     }
 }
 }  // namespace
@@ -482,10 +492,10 @@ extern "C" int lb_softmax_rows(lb_ctx* ctx, const void* x, int64_t ld, int64_t r
 }
 
 extern "C" int lb_postprocess_u8(lb_ctx* ctx, const void* img_nchw, int B, int C, int64_t hw, void* out_u8_nhwc,
-                                 void* stream) {
+                                 int* nonfinite_count_dev, void* stream) {
     LB_REQUIRE(ctx && img_nchw && out_u8_nhwc, "lb_postprocess_u8: null argument");
     lb_launch_pdl(postprocess_u8_kernel, grid_for((long long)B * hw * C, ctx->sm_count), kThreads, 0, lb_stream(stream), 
-        (const __half*)img_nchw, B, C, hw, (uint8_t*)out_u8_nhwc);
+        (const __half*)img_nchw, B, C, hw, (uint8_t*)out_u8_nhwc, nonfinite_count_dev);
     LB_LAUNCH_CHECK();
     return 0;
 }

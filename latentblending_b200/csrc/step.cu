@@ -22,6 +22,19 @@ __global__ void __launch_bounds__(kThreads)
 scale_input_kernel(const __half* __restrict__ x, __half* __restrict__ out, int64_t n, int batch, float divisor) {
     pdl_launch_dependents();
     pdl_wait();
+    if (n % 8 == 0) {                      // 128-bit path (host checked the alignment)
+        const int64_t nv = n / 8;
+        for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < nv; v += (int64_t)gridDim.x * kThreads) {
+            const uint4 vx = reinterpret_cast<const uint4*>(x)[v];
+            const __half* hx = reinterpret_cast<const __half*>(&vx);
+            uint4 vo;
+            __half* ho = reinterpret_cast<__half*>(&vo);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ho[e] = __float2half_rn(__fdiv_rn(__half2float(hx[e]), divisor));
+            for (int b = 0; b < batch; ++b) reinterpret_cast<uint4*>(out + (int64_t)b * n)[v] = vo;
+        }
+        return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
         __half v = __float2half_rn(__fdiv_rn(__half2float(x[i]), divisor));
         for (int b = 0; b < batch; ++b) out[(int64_t)b * n + i] = v;
@@ -50,9 +63,11 @@ __device__ __forceinline__ float step_elem(float x, float eu, float et, float nz
 }
 
 __global__ void __launch_bounds__(kThreads)
-cfg_euler_kernel(const __half* __restrict__ x, const __half* __restrict__ eps, const __half* __restrict__ noise,
+cfg_euler_kernel(const __half* __restrict__ x, const __half* __restrict__ eps, const __half* __restrict__ eps_text,
+                 const __half* __restrict__ noise,
                  __half* __restrict__ out, __half* __restrict__ traj, int64_t n, int use_cfg, float g,
-                 float sigma, float dt, float sigma_up) {
+                 float sigma, float dt, float sigma_up, __half* __restrict__ scaled_next, int scaled_batch,
+                 float next_divisor) {
     pdl_launch_dependents();
     pdl_wait();
     const bool has_noise = noise != nullptr;
@@ -62,7 +77,7 @@ cfg_euler_kernel(const __half* __restrict__ x, const __half* __restrict__ eps, c
         for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < nv; v += (int64_t)gridDim.x * kThreads) {
             uint4 vx = reinterpret_cast<const uint4*>(x)[v];
             uint4 vu = lb_ldg_stream(reinterpret_cast<const uint4*>(eps) + v);
-            uint4 vt = use_cfg ? lb_ldg_stream(reinterpret_cast<const uint4*>(eps + n) + v) : vu;
+            uint4 vt = use_cfg ? lb_ldg_stream(reinterpret_cast<const uint4*>(eps_text) + v) : vu;
             uint4 vn = has_noise ? lb_ldg_stream(reinterpret_cast<const uint4*>(noise) + v) : make_uint4(0, 0, 0, 0);
             const __half* hx = reinterpret_cast<const __half*>(&vx);
             const __half* hu = reinterpret_cast<const __half*>(&vu);
@@ -77,14 +92,25 @@ cfg_euler_kernel(const __half* __restrict__ x, const __half* __restrict__ eps, c
                                                   sigma_up));
             reinterpret_cast<uint4*>(out)[v] = vo;
             if (traj) reinterpret_cast<uint4*>(traj)[v] = vo;
+            if (scaled_next) {               // next step's scale_model_input + CFG duplicate, same roundings as the op
+                uint4 vs;
+                __half* hs = reinterpret_cast<__half*>(&vs);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) hs[e] = __float2half_rn(__fdiv_rn(__half2float(ho[e]), next_divisor));
+                for (int b = 0; b < scaled_batch; ++b) reinterpret_cast<uint4*>(scaled_next + (int64_t)b * n)[v] = vs;
+            }
         }
     } else {
         for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
             float r = step_elem(__half2float(x[i]), __half2float(eps[i]),
-                                use_cfg ? __half2float(eps[n + i]) : 0.f, has_noise ? __half2float(noise[i]) : 0.f,
+                                use_cfg ? __half2float(eps_text[i]) : 0.f, has_noise ? __half2float(noise[i]) : 0.f,
                                 use_cfg != 0, has_noise, g, sigma, dt, sigma_up);
             out[i] = __float2half_rn(r);
             if (traj) traj[i] = __float2half_rn(r);
+            if (scaled_next) {
+                const __half sv = __float2half_rn(__fdiv_rn(__half2float(__float2half_rn(r)), next_divisor));
+                for (int b = 0; b < scaled_batch; ++b) scaled_next[(int64_t)b * n + i] = sv;
+            }
         }
     }
 }
@@ -96,7 +122,8 @@ extern "C" int lb_scale_model_input(lb_ctx* ctx, const void* latents, void* out,
     LB_REQUIRE(ctx != nullptr, "lb_scale_model_input: null context");
     LB_REQUIRE(latents && out, "lb_scale_model_input: null buffer");
     LB_REQUIRE(batch >= 1 && n > 0, "lb_scale_model_input: bad sizes");
-    unsigned grid = (unsigned)lb_ceil_div(n, kThreads);
+    if (n % 8 == 0) LB_REQUIRE(lb_aligned16(latents) && lb_aligned16(out), "lb_scale_model_input: 16-byte alignment");
+    unsigned grid = (unsigned)lb_ceil_div(n, n % 8 == 0 ? (int64_t)kThreads * 8 : (int64_t)kThreads);
     if (grid > 148 * 8) grid = 148 * 8;
     lb_launch_pdl(scale_input_kernel, grid, kThreads, 0, lb_stream(stream), (const __half*)latents, (__half*)out, n, batch,
                                                                 divisor);
@@ -104,22 +131,30 @@ extern "C" int lb_scale_model_input(lb_ctx* ctx, const void* latents, void* out,
     return 0;
 }
 
-extern "C" int lb_cfg_euler_step(lb_ctx* ctx, const void* latents, const void* eps, const void* noise, void* out,
+extern "C" int lb_cfg_euler_step(lb_ctx* ctx, const void* latents, const void* eps, const void* eps_text,
+                                 const void* noise, void* out,
                                  void* traj, int64_t n, int use_cfg, float guidance, float sigma, float dt,
-                                 float sigma_up, void* stream) {
+                                 float sigma_up, void* scaled_next, int scaled_batch, float next_divisor,
+                                 void* stream) {
     LB_REQUIRE(ctx != nullptr, "lb_cfg_euler_step: null context");
     LB_REQUIRE(latents && eps && out, "lb_cfg_euler_step: null buffer");
     LB_REQUIRE(n > 0, "lb_cfg_euler_step: n must be positive");
+    LB_REQUIRE(!scaled_next || (scaled_batch >= 1 && next_divisor > 0.f), "lb_cfg_euler_step: scaled_next needs a batch "
+               "and a positive divisor");
     if (n % 8 == 0)
         LB_REQUIRE(lb_aligned16(latents) && lb_aligned16(eps) && lb_aligned16(out) &&
-                       (!noise || lb_aligned16(noise)) && (!traj || lb_aligned16(traj)),
+                       (!noise || lb_aligned16(noise)) && (!traj || lb_aligned16(traj)) &&
+                       (!scaled_next || lb_aligned16(scaled_next)),
                    "lb_cfg_euler_step: buffers must be 16-byte aligned");
     unsigned grid = (unsigned)lb_ceil_div(n, (int64_t)kThreads * 8);
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
-    lb_launch_pdl(cfg_euler_kernel, grid, kThreads, 0, lb_stream(stream), (const __half*)latents, (const __half*)eps,
+    const __half* et = eps_text ? (const __half*)eps_text : (const __half*)eps + n;   // default: [2,n] = (uncond, text)
+    LB_REQUIRE(n % 8 != 0 || lb_aligned16(et), "lb_cfg_euler_step: eps_text must be 16-byte aligned");
+    lb_launch_pdl(cfg_euler_kernel, grid, kThreads, 0, lb_stream(stream), (const __half*)latents, (const __half*)eps, et,
                                                               (const __half*)noise, (__half*)out, (__half*)traj, n,
-                                                              use_cfg, guidance, sigma, dt, sigma_up);
+                                                              use_cfg, guidance, sigma, dt, sigma_up,
+                                                              (__half*)scaled_next, scaled_batch, next_divisor);
     LB_LAUNCH_CHECK();
     return 0;
 }

@@ -46,6 +46,11 @@ class DiffusersHolder:
         self.noise_fn_multi = None    # same for run_diffusion_sd_xl_multi with k > 1: noise_fn_multi(job, i, shape)
         self._cond_key = None
         self.n_unet_calls = 0
+        # multi-GPU CFG split (latentblending_b200/sharding.py): dict(group=<2-rank process group>, half=0|1) makes this
+        # rank compute only the unconditional (0) or the text (1) half of every CFG batch; the halves' eps are
+        # exchanged once per step (one all-gather of k x 128 KB over NVLink), then both ranks take the identical step.
+        self.cfg_split = None
+        self._eps_pair = {}
 
     # ---- configuration --------------------------------------------------------------------
     def set_num_inference_steps(self, num_inference_steps):
@@ -85,6 +90,10 @@ class DiffusersHolder:
     def decode_to_device(self, latents):
         """latents [1,4,h,w] -> uint8 [H,W,3] frame on the device."""
         return self.vae.decode_to_u8(latents.to(torch.float16))
+
+    def check_decode_overflow(self):
+        if self.vae.decodes_since_check:
+            self.vae.check_overflow()
 
     @torch.no_grad()
     def latent2image(self, latents, output_type="pil"):
@@ -144,13 +153,17 @@ class DiffusersHolder:
         cfg_on = self.guidance_scale > 1                       # pipe.do_classifier_free_guidance
         hw = self.pipe.default_sample_size * self.pipe.vae_scale_factor   # original/target size, :216-220
         tid = torch.tensor([[hw, hw, 0, 0, hw, hw]], dtype=torch.float16, device=self.device)
-        Bj = 2 if cfg_on else 1
+        split = self.cfg_split if cfg_on else None           # without CFG there is nothing to split
+        Bj = 1 if (split is not None or not cfg_on) else 2      # UNet batch rows per job ON THIS RANK
         k = len(jobs)
         _, C, h, w = jobs[0]["latents_start"].shape
         ctxs, texts = [], []
         for job in jobs:
             pe, ne, pp, npool = job["text_embeddings"]
-            if cfg_on:
+            if split is not None:
+                ctxs.append(pe if split["half"] else ne)
+                texts.append(pp if split["half"] else npool)
+            elif cfg_on:
                 ctxs += [ne, pe]
                 texts += [npool, pp]
             else:
@@ -160,6 +173,12 @@ class DiffusersHolder:
         plan.ctx.copy_(torch.cat(ctxs, dim=0).reshape(plan.ctx.shape))
         plan.text.copy_(torch.cat(texts, dim=0))
         plan.tids.copy_(tid.expand(Bj * k, -1))
+        eps_pair = None
+        if split is not None:
+            key = (k, C, h, w)
+            if key not in self._eps_pair:
+                self._eps_pair[key] = torch.empty((2, k, C, h, w), dtype=torch.float16, device=self.device)
+            eps_pair = self._eps_pair[key]
         plan.prog_ctx.run()                                    # cross-attention K/V: once per conditioning
         n = C * h * w
         outs = [[None] * N for _ in jobs]
@@ -173,6 +192,14 @@ class DiffusersHolder:
             mixing.append(m)
             guidance.append(job.get("guidance_scale", self.guidance_scale))
             latents.append(None)
+        # Ancestral schedulers draw one noise tensor per step from the global RNG.  The reference (and the sequential
+        # path) runs trajectory 1 to the end before trajectory 2, so under torch.manual_seed the draws are ordered
+        # job-major; the lockstep loop consumes them step-major.  Pre-draw them in the reference's order.
+        drawn = None
+        if sched.ancestral and k > 1 and self.noise_fn_multi is None and self.noise_fn is None:
+            drawn = [[torch.randn((1, C, h, w), device=self.device, dtype=torch.float16) for _ in range(idx_start, N)]
+                     for _ in jobs]
+        scaled = [False] * k          # the previous step's lb_cfg_euler_step already wrote this job's model input
         for i in range(N):
             if i < idx_start:
                 continue
@@ -183,9 +210,14 @@ class DiffusersHolder:
                 if i > 0 and coeffs[j][i] > 0:
                     latents[j] = ops.slerp_rows(latents[j].view(1, n), mixing[j][i - 1].reshape(1, n),
                                                 float(coeffs[j][i])).view(1, C, h, w)
-                ops.scale_model_input(latents[j], Bj, sc["divisor"], out=plan.x_in[j * Bj:(j + 1) * Bj])
+                    scaled[j] = False
+                if not scaled[j]:
+                    ops.scale_model_input(latents[j], Bj, sc["divisor"], out=plan.x_in[j * Bj:(j + 1) * Bj])
             plan.prog_step.run(sc["t"])
             self.n_unet_calls += 1
+            if eps_pair is not None:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(eps_pair, plan.eps, group=split["group"])   # [uncond | text] x k jobs
             for j in range(k):
                 noise = None
                 if sched.ancestral:
@@ -195,11 +227,20 @@ class DiffusersHolder:
                     elif self.noise_fn is not None:
                         noise = self.noise_fn(i, latents[j].shape).to(device=self.device,
                                                                       dtype=torch.float16).contiguous()
+                    elif drawn is not None:
+                        noise = drawn[j][i - idx_start]
                     else:
                         noise = torch.randn(latents[j].shape, device=self.device, dtype=torch.float16)
                 new = trajs[j][i:i + 1]
-                ops.cfg_euler_step(latents[j], plan.eps[j * Bj:(j + 1) * Bj], guidance[j], sc["sigma"], sc["dt"],
-                                   sc["sigma_up"], noise=noise, out=new)
+                # fold the NEXT step's scale_model_input (+ CFG duplicate) into this launch unless a crossfeed mix
+                # sits in between (diffusers_holder.py:322-330 order: mix, then scale)
+                fuse = i + 1 < N and not (coeffs[j][i + 1] > 0)
+                ops.cfg_euler_step(latents[j], plan.eps[j * Bj:(j + 1) * Bj] if eps_pair is None else eps_pair[0, j],
+                                   guidance[j], sc["sigma"], sc["dt"], sc["sigma_up"], noise=noise, out=new,
+                                   eps_text=None if eps_pair is None else eps_pair[1, j],
+                                   scaled_next=plan.x_in[j * Bj:(j + 1) * Bj] if fuse else None,
+                                   next_divisor=sched.step_scalars[i + 1]["divisor"] if fuse else 0.0)
+                scaled[j] = fuse
                 latents[j] = new
                 outs[j][i] = new
         return outs

@@ -82,19 +82,29 @@ def scale_model_input(latents, batch, divisor, out=None):
     return out
 
 
-def cfg_euler_step(latents, eps, guidance, sigma, dt, sigma_up=0.0, noise=None, out=None, traj=None):
-    """eps: [2,...] (uncond, text) when CFG is on else [1,...]."""
+def cfg_euler_step(latents, eps, guidance, sigma, dt, sigma_up=0.0, noise=None, out=None, traj=None,
+                   scaled_next=None, next_divisor=0.0, eps_text=None):
+    """eps: [2,...] (uncond, text) when CFG is on else [1,...]; or eps = uncond half and eps_text = text half
+    (separate buffers).  ``scaled_next`` ([batch, ...] fp16): also write the
+    next step's model input fp16(x_new / next_divisor) replicated over its batch (the next scale_model_input)."""
     assert latents.dtype == torch.float16 and eps.dtype == torch.float16
     assert latents.is_contiguous() and eps.is_contiguous()
     dev = _dev(latents)
     n = latents.numel()
-    use_cfg = eps.numel() == 2 * n
+    use_cfg = eps.numel() == 2 * n or eps_text is not None
     assert use_cfg or eps.numel() == n
+    if eps_text is not None:
+        assert eps_text.dtype == torch.float16 and eps_text.is_contiguous() and eps_text.numel() == n
     if out is None:
         out = torch.empty_like(latents)
-    check(_cabi.load().lb_cfg_euler_step(ctx(dev), ptr(latents), ptr(eps), ptr(noise), ptr(out), ptr(traj), n,
+    sb = 0
+    if scaled_next is not None:
+        assert scaled_next.dtype == torch.float16 and scaled_next.is_contiguous() and scaled_next.numel() % n == 0
+        sb = scaled_next.numel() // n
+    check(_cabi.load().lb_cfg_euler_step(ctx(dev), ptr(latents), ptr(eps), ptr(eps_text), ptr(noise), ptr(out), ptr(traj), n,
                                          int(use_cfg), float(np.float32(guidance)), float(sigma), float(dt),
-                                         float(sigma_up), stream_ptr()), "lb_cfg_euler_step")
+                                         float(sigma_up), ptr(scaled_next), sb, float(next_divisor), stream_ptr()),
+          "lb_cfg_euler_step")
     LAUNCHES[0] += 1
     return out
 
@@ -104,7 +114,7 @@ def _p(t):
 
 
 def gemm(a0, w, N, B, H, W, taps=1, a0_c=None, a1=None, a1_c=None, bias=None, bias2=None, res=None, out=None,
-         mode=0, out_cols=None, static_w=False):
+         mode=0, out_cols=None, static_w=False, relu=False, ln=None, stats_out=None):
     """Tensor-core GEMM / implicit-GEMM conv (lb_gemm).  a0: NHWC activation viewed as
     [B*H*W, >=a0_c] (row stride = a0.stride(0)); w: [N, K] packed weights."""
     dev = _dev(a0)
@@ -124,8 +134,53 @@ def gemm(a0, w, N, B, H, W, taps=1, a0_c=None, a1=None, a1_c=None, bias=None, bi
         d.bias2, d.bias2_ld = _p(bias2), bias2.stride(0)
     if res is not None:
         d.res, d.res_ld = _p(res), res.stride(-2)
-    d.out, d.out_ld, d.mode = _p(out), out.stride(-2), mode | (_cabi.GEMM_STATIC_W if static_w else 0)
+    d.out, d.out_ld = _p(out), out.stride(-2)
+    d.mode = mode | (_cabi.GEMM_STATIC_W if static_w else 0) | (_cabi.GEMM_RELU if relu else 0)
+    if ln is not None:
+        d.ln_stats, d.ln_parts = _p(ln["stats"]), ln["stats"].shape[1]
+        d.ln_csum, d.ln_bias, d.ln_eps = _p(ln["csum"]), _p(ln["bias"]), ln["eps"]
+    if stats_out is not None:
+        d.stats_out, d.stats_parts = _p(stats_out), stats_out.shape[1]
     check(_cabi.load().lb_gemm(ctx(dev), d, stream_ptr()), "lb_gemm")
+    return out
+
+
+def gemm_stats_parts(a0, w, N, B, H, W, **kw):
+    """Per-row partial count of lb_gemm's stats_out for this problem (2 per N tile)."""
+    import ctypes
+    dev = _dev(a0)
+    d = _cabi.GemmDesc()
+    M = B * H * W
+    out = torch.empty((M, N), dtype=torch.float16, device=a0.device)
+    d.a0, d.a0_ld, d.a0_c = _p(a0), a0.stride(-2), kw.get("a0_c") or a0.shape[-1]
+    d.B, d.H, d.W, d.taps = B, H, W, kw.get("taps", 1)
+    d.w, d.w_ld, d.N = _p(w), w.stride(0), N
+    d.out, d.out_ld, d.mode = _p(out), out.stride(-2), kw.get("mode", 0)
+    return int(_cabi.load().lb_gemm_stats_parts(ctx(dev), ctypes.byref(d)))
+
+
+def lpips_tap(feat_a, feat_b, lin_w, out_scalar, workspace, accumulate=False):
+    """One LPIPS tap reduction over [pixels, C] fp16 feature matrices (lb_lpips_tap)."""
+    dev = _dev(feat_a)
+    assert feat_a.shape == feat_b.shape and feat_a.stride(0) == feat_b.stride(0) and feat_a.dtype == torch.float16
+    rows, C = feat_a.shape
+    check(_cabi.load().lb_lpips_tap(ctx(dev), ptr(feat_a), ptr(feat_b), feat_a.stride(0), rows, C, ptr(lin_w),
+                                    int(accumulate), ptr(out_scalar), ptr(workspace), stream_ptr()), "lb_lpips_tap")
+    LAUNCHES[0] += 2
+    return out_scalar
+
+
+def frames_lerp_u8(frames, left, w0, w1, out=None):
+    """frames [F, n] uint8 (contiguous); left int32 [T], w0/w1 float32 [T] on the device -> [T, n] uint8
+    (lb_frames_lerp_u8: numpy-float32 blend with truncating uint8 cast)."""
+    dev = _dev(frames)
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames.dim() == 2
+    T = left.numel()
+    if out is None:
+        out = torch.empty((T, frames.shape[1]), dtype=torch.uint8, device=frames.device)
+    check(_cabi.load().lb_frames_lerp_u8(ctx(dev), ptr(frames), frames.shape[1], ptr(left), ptr(w0), ptr(w1), T,
+                                         ptr(out), stream_ptr()), "lb_frames_lerp_u8")
+    LAUNCHES[0] += 1
     return out
 
 

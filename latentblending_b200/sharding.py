@@ -18,9 +18,17 @@ never on branches of its own level.  So within a level:
               first miss starts the next round.  Mis-speculated branches stay cached for later
               rounds of the level and are dropped at its end.
 
-The tree that results is exactly the sequential one (same ``tree_fracts`` order, same parents):
-the similarity pair of every insertion is taken from rank 0 so all replicas take identical
-decisions.  There is no data-path collective other than the per-round all-gather.
+The tree that results is exactly the sequential one (same ``tree_fracts`` order, same parents).
+Every rank evaluates the similarity pair of every insertion itself on the replicated (all-gathered)
+frames: the metric kernels are deterministic, so all replicas take identical decisions without any
+further collective (a one-word agreement check per level guards that assumption).
+
+CFG split ("GPU pair per branch splitting the CFG halves"): with classifier-free
+guidance every UNet forward is a batch of two (unconditional, text).  When there are more ranks than
+useful candidates the ranks pair up into TEAMS of two: each team computes ONE candidate, each member one
+CFG half (a batch-1 forward, ~0.6x the time of the batch-2 one), and the two 128 KB eps halves are
+exchanged once per step inside the team (DiffusersHolder.cfg_split).  The per-round all-gather then takes
+each team's slab from its first member.
 
 This module is pure host logic + collectives; the arithmetic is injected (``compute``,
 ``similarity``), which is how the world_size-2 gloo test drives it on CPU.
@@ -78,11 +86,32 @@ class LevelSharder:
     similarity(frame_a, frame_b) -> float
     """
 
-    def __init__(self, rank, world, group=None, device=None):
+    def __init__(self, rank, world, group=None, device=None, cfg_pairs=False):
         self.rank, self.world, self.group = rank, world, group
         self.device = device
-        self.stats = dict(rounds=0, computed=0, used=0)
+        self.stats = dict(rounds=0, computed=0, used=0, paired_rounds=0)
         self.split_ratio = 0.6        # running estimate of (similarity of a half) / (similarity of the split gap)
+        self.cfg_pairs = bool(cfg_pairs) and world >= 2     # CFG is on: ranks may pair up (one CFG half each)
+        self._pair_groups = None
+
+    # -- teams ---------------------------------------------------------------------------------
+    def team_size(self, remaining):
+        """Ranks per candidate this round.  Pairs (one CFG half per rank: a batch-1 forward costs ~0.6x a batch-2 one)
+        whenever the ranks outnumber what speculation can use: always from 4 ranks up (levels have few stems and the
+        hit rate of the 3rd, 4th, ... speculative candidate is low), and on 2 ranks for the last stem of a level."""
+        if not self.cfg_pairs:
+            return 1
+        if self.world >= 4:
+            return 2
+        return 2 if remaining <= 1 else 1
+
+    def pair_group(self):
+        """The 2-rank process group of this rank's team; all groups are created collectively on first use."""
+        import torch.distributed as dist
+        if self._pair_groups is None:
+            self._pair_groups = [dist.new_group(ranks=[2 * t, 2 * t + 1]) for t in range(self.world // 2)]
+        t = self.rank // 2
+        return self._pair_groups[t] if t < len(self._pair_groups) else None
 
     # -- collectives -------------------------------------------------------------------------
     def _all_gather(self, t):
@@ -91,24 +120,39 @@ class LevelSharder:
         dist.all_gather(outs, t.contiguous(), group=self.group)
         return outs
 
-    def _bcast_pair(self, a, b):
+    def _check_agreement(self, tree):
+        """All replicas must hold the same tree (they decide independently on replicated data)."""
         import torch.distributed as dist
-        t = torch.tensor([a, b], dtype=torch.float64, device=self.device if self.device is not None else "cpu")
-        dist.broadcast(t, src=0, group=self.group)
-        return float(t[0]), float(t[1])
+        v = float(np.sum(np.asarray(tree.tree_fracts, dtype=np.float64) * np.arange(1, len(tree.tree_fracts) + 1)))
+        t = torch.tensor([v, -v], dtype=torch.float64, device=self.device if self.device is not None else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        if float(t[0]) != -float(t[1]):
+            raise RuntimeError("sharded transition: the ranks' trees diverged (non-deterministic similarity?)")
 
     # -- one level ---------------------------------------------------------------------------------
-    def run_level(self, tree, idx_injection, n_stems, compute, similarity, num_steps):
+    def run_level(self, tree, idx_injection, n_stems, compute, similarity, num_steps, on_insert=None):
+        """``on_insert(mid)`` runs on EVERY rank for every inserted branch, in insertion order (state the sequential
+        engine updates per branch -- the guidance dampening -- must end up identical on all ranks)."""
         cache = {}                # mid -> (list_latents, frame)
         remaining = int(n_stems)
         while remaining > 0:
-            cands = plan_candidates(tree.tree_fracts, tree.tree_similarities, self.world, cache, self.split_ratio)
+            team = self.team_size(remaining)
+            n_teams = self.world // team
+            cands = plan_candidates(tree.tree_fracts, tree.tree_similarities, n_teams, cache, self.split_ratio)
             self.stats["rounds"] += 1
-            mine = cands[self.rank] if self.rank < len(cands) else None
+            self.stats["paired_rounds"] += int(team == 2)
+            my_team = self.rank // team
+            mine = cands[my_team] if my_team < len(cands) and self.rank < n_teams * team else None
             slab = frame = None
+            if team == 2:
+                self.pair_group()              # collective creation on first use: every rank must get here
             if mine is not None:
                 p1, p2 = older_parents(tree.tree_fracts, tree.tree_idx_injection, mine[0], idx_injection)
-                traj, frame = compute(mine[0], p1, p2, idx_injection)
+                if team == 2:
+                    traj, frame = compute(mine[0], p1, p2, idx_injection,
+                                          cfg_split=dict(group=self.pair_group(), half=self.rank % 2))
+                else:
+                    traj, frame = compute(mine[0], p1, p2, idx_injection)
                 slab = torch.stack([t.reshape(-1) for t in traj[idx_injection:]], 0)
             # shapes are identical on every rank that has work; idle ranks send zeros of the same shape
             ref_shape = self._agree_shapes(slab, frame, tree, idx_injection, num_steps)
@@ -118,7 +162,8 @@ class LevelSharder:
             slabs = self._all_gather(slab)
             frames = self._all_gather(frame)
             lat_shape = tree.tree_latents[0][-1].shape
-            for r, (mid, lo, hi) in enumerate(cands):
+            for c, (mid, lo, hi) in enumerate(cands):
+                r = c * team                   # a team's slab is taken from its first member (both hold the same data)
                 traj = [None] * idx_injection + [slabs[r][i].view(lat_shape) for i in range(num_steps - idx_injection)]
                 cache[mid] = (traj, frames[r])
                 self.stats["computed"] += 1
@@ -132,11 +177,12 @@ class LevelSharder:
                 traj, frm = cache.pop(mid)
                 left = similarity(frm, tree.frames[c1])
                 right = similarity(frm, tree.frames[c1 + 1])
-                left, right = self._bcast_pair(left, right)
                 parent_sim = sims[c1]
                 if isinstance(parent_sim, (int, float, np.floating)) and parent_sim > 0:
                     obs = min(1.0, max(left, right) / float(parent_sim))
                     self.split_ratio = 0.7 * self.split_ratio + 0.3 * obs     # identical on every rank
+                if on_insert is not None:
+                    on_insert(mid)
                 k = c1 + 1
                 tree.tree_latents.insert(k, traj)
                 tree.frames.insert(k, frm)
@@ -146,6 +192,7 @@ class LevelSharder:
                 tree.tree_similarities.insert(k, right)
                 remaining -= 1
                 self.stats["used"] += 1
+        self._check_agreement(tree)
 
     def _agree_shapes(self, slab, frame, tree, idx_injection, num_steps):
         lat = tree.tree_latents[0][-1]

@@ -26,9 +26,10 @@ from typing import Tuple
 import torch
 
 from . import _cabi
-from ._cabi import (GEMM_STATIC_W, OP_ATTENTION, OP_CONV_IN, OP_CONV_OUT, OP_EMBED_INPUTS, OP_GEMM, OP_GROUPNORM, OP_IM2COL_S2,
-                    OP_LATENT_PREP, OP_LAYERNORM, OP_LINEAR_SMALL, OP_POSTPROCESS_U8, OP_SOFTMAX_ROWS, OP_UPSAMPLE2X,
-                    Op, check, ctx, stream_ptr)
+from ._cabi import (GEMM_RELU, GEMM_STATIC_W, OP_ATTENTION, OP_CONV_IN, OP_CONV_OUT, OP_EMBED_INPUTS, OP_GEMM,
+                    OP_GROUPNORM, OP_IM2COL, OP_IM2COL_S2, OP_LATENT_PREP, OP_LAYERNORM, OP_LINEAR_SMALL,
+                    OP_LPIPS_IM2COL_U8, OP_MAXPOOL3S2, OP_POSTPROCESS_U8, OP_SOFTMAX_ROWS, OP_UPSAMPLE2X, Op, check, ctx,
+                    stream_ptr)
 
 
 @dataclass
@@ -79,10 +80,13 @@ class Program:
 
     # -- op emitters (mirror latentblending_b200.ops, but record instead of launching) --------
     def gemm(self, a0, w, N, B, H, W, out, taps=1, a0_c=None, a1=None, a1_c=None, bias=None, bias2=None, res=None,
-             mode=0, static_w=True):
+             mode=0, static_w=True, relu=False, ln=None, stats_out=None):
         """``static_w``: ``w`` holds model weights (not written by the preceding op), so the kernel may fetch its
         first tiles before the preceding kernel has finished (LB_GEMM_STATIC_W).  Pass False when an activation
-        is used as the B operand."""
+        is used as the B operand.
+        ``ln``: dict(stats=[M,parts,2] fp32, csum=[N] fp32, bias=[N] fp32, eps) -- LayerNorm folded into this GEMM
+        (``w`` must already hold w*gamma; see include/lb200.h).  ``stats_out``: [M,parts,2] fp32 buffer that receives
+        this GEMM's per-row partial sums for a following LN-folded GEMM (parts = self.gemm_stats_parts(...))."""
         d = self._new(OP_GEMM).u.gemm
         d.a0, d.a0_ld, d.a0_c = _p(a0), a0.stride(0), (a0.shape[1] if a0_c is None else a0_c)
         if a1 is not None:
@@ -94,8 +98,47 @@ class Program:
             d.bias2, d.bias2_ld = _p(bias2), bias2.stride(0)
         if res is not None:
             d.res, d.res_ld = _p(res), res.stride(0)
-        d.out, d.out_ld, d.mode = _p(out), out.stride(0), mode | (GEMM_STATIC_W if static_w else 0)
+        d.out, d.out_ld = _p(out), out.stride(0)
+        d.mode = mode | (GEMM_STATIC_W if static_w else 0) | (GEMM_RELU if relu else 0)
+        if ln is not None:
+            st = ln["stats"]
+            assert st.dtype == torch.float32 and st.dim() == 3 and st.shape[2] == 2 and st.is_contiguous()
+            d.ln_stats, d.ln_parts = _p(st), st.shape[1]
+            d.ln_csum, d.ln_bias, d.ln_eps = _p(ln["csum"]), _p(ln["bias"]), ln["eps"]
+            self.hold(st, ln["csum"], ln["bias"])
+        if stats_out is not None:
+            assert stats_out.dtype == torch.float32 and stats_out.dim() == 3 and stats_out.is_contiguous()
+            d.stats_out, d.stats_parts = _p(stats_out), stats_out.shape[1]
+            self.hold(stats_out)
         self.hold(a0, w, a1, bias, bias2, res, out)
+
+    def gemm_stats_parts(self, a0, w, N, B, H, W, out, **kw):
+        """Number of per-row partials a GEMM with these arguments writes through ``stats_out``."""
+        probe = Program(self.dev)
+        probe.gemm(a0, w, N, B, H, W, out, **kw)
+        n = int(_cabi.load().lb_gemm_stats_parts(ctx(self.dev), ctypes.byref(probe.ops[0].u.gemm)))
+        if n < 0:
+            raise _cabi.LB200Error("lb_gemm_stats_parts failed: " + _cabi.load().lb_last_error().decode())
+        return n
+
+    def lpips_im2col_u8(self, frame_u8, H, W, k, stride, pad, shift, scale, out):
+        d = self._new(OP_LPIPS_IM2COL_U8).u.patch
+        d.x, d.H, d.W, d.C, d.k, d.stride, d.pad = _p(frame_u8), H, W, out.shape[1], k, stride, pad
+        d.out, d.ld_out = _p(out), out.stride(0)
+        for i in range(3):
+            d.f[i], d.f[3 + i] = shift[i], scale[i]
+        self.hold(frame_u8, out)
+
+    def im2col(self, x, H, W, C, k, stride, pad, out):
+        d = self._new(OP_IM2COL).u.patch
+        d.x, d.ld_x, d.H, d.W, d.C, d.k, d.stride, d.pad = _p(x), x.stride(0), H, W, C, k, stride, pad
+        d.out, d.ld_out = _p(out), out.stride(0)
+        self.hold(x, out)
+
+    def maxpool3s2(self, x, H, W, C, out):
+        d = self._new(OP_MAXPOOL3S2).u.patch
+        d.x, d.ld_x, d.H, d.W, d.C, d.out, d.ld_out = _p(x), x.stride(0), H, W, C, _p(out), out.stride(0)
+        self.hold(x, out)
 
     def attention(self, q, k, v, out, B, heads, Sq, Skv, q_col0=0, k_col0=0, v_col0=0, scale=0.125):
         d = self._new(OP_ATTENTION).u.attn
@@ -168,11 +211,11 @@ class Program:
         d.x, d.ld_x, d.out, d.ld_out, d.n, d.C = _p(x), x.stride(0), _p(out), out.stride(0), x.shape[0], x.shape[1]
         self.hold(x, out)
 
-    def postprocess_u8(self, img_nchw, out_u8):
+    def postprocess_u8(self, img_nchw, out_u8, nonfinite=None):
         d = self._new(OP_POSTPROCESS_U8).u.aux
         B, C, H, W = img_nchw.shape
-        d.x, d.out, d.n, d.B, d.C = _p(img_nchw), _p(out_u8), H * W, B, C
-        self.hold(img_nchw, out_u8)
+        d.x, d.out, d.n, d.B, d.C, d.w = _p(img_nchw), _p(out_u8), H * W, B, C, _p(nonfinite)
+        self.hold(img_nchw, out_u8, nonfinite)
 
     # -- lifecycle --------------------------------------------------------------------------
     def finalize(self):
@@ -220,6 +263,16 @@ class Program:
             pass
 
 
+def _fold_layernorm(w, bias, gamma, beta):
+    """(w*gamma in fp16, rowsum of THAT in fp32, w beta + bias in fp32) for the LayerNorm-folded GEMM."""
+    wf = (w.float() * gamma.float()[None, :]).half().contiguous()
+    csum = wf.float().sum(dim=1).contiguous()
+    lnb = w.float() @ beta.float()
+    if bias is not None:
+        lnb = lnb + bias.float()
+    return wf, csum, lnb.contiguous()
+
+
 def _geglu_perm(inner, device):
     idx = torch.arange(inner, device=device).view(-1, 64)
     return torch.stack([idx, idx + inner], dim=1).reshape(-1)
@@ -228,9 +281,10 @@ def _geglu_perm(inner, device):
 class PackedUNet:
     """fp16 device copies of the UNet parameters in the layouts the kernels consume."""
 
-    def __init__(self, cfg: UNetConfig, state_dict, device):
+    def __init__(self, cfg: UNetConfig, state_dict, device, fold_ln=True):
         self.cfg = cfg
         self.device = torch.device(device)
+        self.fold_ln = fold_ln
         sd = state_dict
         dev = self.device
 
@@ -286,15 +340,26 @@ class PackedUNet:
                 t = f"{a}.transformer_blocks.{depth}"
                 for n in ("norm1", "norm2", "norm3"):
                     W[f"{t}.{n}.g"], W[f"{t}.{n}.b"] = g(f"{t}.{n}.weight"), g(f"{t}.{n}.bias")
-                W[t + ".attn1.qkv.w"] = torch.cat([g(t + ".attn1.to_q.weight"), g(t + ".attn1.to_k.weight"),
-                                                    g(t + ".attn1.to_v.weight")], 0).contiguous()
+                wqkv = torch.cat([g(t + ".attn1.to_q.weight"), g(t + ".attn1.to_k.weight"),
+                                  g(t + ".attn1.to_v.weight")], 0).contiguous()
                 W[t + ".attn1.out.w"], W[t + ".attn1.out.b"] = g(t + ".attn1.to_out.0.weight"), g(t + ".attn1.to_out.0.bias")
-                W[t + ".attn2.q.w"] = g(t + ".attn2.to_q.weight")
+                wq = g(t + ".attn2.to_q.weight")
                 W[t + ".attn2.kv.w"] = torch.cat([g(t + ".attn2.to_k.weight"), g(t + ".attn2.to_v.weight")], 0).contiguous()
                 W[t + ".attn2.out.w"], W[t + ".attn2.out.b"] = g(t + ".attn2.to_out.0.weight"), g(t + ".attn2.to_out.0.bias")
                 pw, pb = g(t + ".ff.net.0.proj.weight"), g(t + ".ff.net.0.proj.bias")
                 perm = _geglu_perm(pw.shape[0] // 2, dev)
-                W[t + ".ff.in.w"], W[t + ".ff.in.b"] = pw[perm].contiguous(), pb[perm].contiguous()
+                if fold_ln:
+                    # LayerNorm folded into the consuming GEMM (include/lb200.h): w' = w*gamma, csum = rowsum(w'),
+                    # lnb = w beta + bias
+                    for key, w_, b_, nrm, pm in ((".attn1.qkv", wqkv, None, "norm1", None), (".attn2.q", wq, None, "norm2", None),
+                                                 (".ff.in", pw, pb, "norm3", perm)):
+                        wf, cs, lb = _fold_layernorm(w_, b_, W[f"{t}.{nrm}.g"], W[f"{t}.{nrm}.b"])
+                        if pm is not None:
+                            wf, cs, lb = wf[pm].contiguous(), cs[pm].contiguous(), lb[pm].contiguous()
+                        W[t + key + ".w"], W[t + key + ".csum"], W[t + key + ".lnb"] = wf, cs, lb
+                else:
+                    W[t + ".attn1.qkv.w"], W[t + ".attn2.q.w"] = wqkv, wq
+                    W[t + ".ff.in.w"], W[t + ".ff.in.b"] = pw[perm].contiguous(), pb[perm].contiguous()
                 W[t + ".ff.out.w"], W[t + ".ff.out.b"] = g(t + ".ff.net.2.weight"), g(t + ".ff.net.2.bias")
                 depth += 1
             W[a + ".depth"] = depth
@@ -310,11 +375,15 @@ class PackedUNet:
 class UNetB200:
     """One lowered forward per (batch, h, w); ``forward`` replays it."""
 
-    def __init__(self, cfg: UNetConfig, state_dict, device="cuda:0"):
+    def __init__(self, cfg: UNetConfig, state_dict, device="cuda:0", fold_ln=None):
+        import os
         self.cfg = cfg
         self.device = torch.device(device)
         self.dev_index = self.device.index or 0
-        self.packed = PackedUNet(cfg, state_dict, self.device)
+        if fold_ln is None:
+            fold_ln = os.environ.get("LB_NO_LN_FOLD") is None
+        self.fold_ln = fold_ln
+        self.packed = PackedUNet(cfg, state_dict, self.device, fold_ln=fold_ln)
         self._plans = {}
 
     # -- public -----------------------------------------------------------------------------
@@ -440,6 +509,9 @@ class _Lowering:
 
         kv_cache = {}
 
+        fold = net.fold_ln
+        f32 = dict(dtype=torch.float32, device=dev)
+
         def transformer(aname, x, C, level, out):
             h_, w_ = res_hw[level]
             S = h_ * w_
@@ -448,26 +520,51 @@ class _Lowering:
             tn = scratch("tn", M, C)
             P.groupnorm(x, B, S, C, groups, Wt[aname + ".norm.g"], Wt[aname + ".norm.b"], 1e-6, 0, tn, self.ws)
             hs = scratch("hs", M, C)
-            P.gemm(tn, Wt[aname + ".proj_in.w"], C, 1, 1, M, hs, bias=Wt[aname + ".proj_in.b"])
+            if not fold:
+                P.gemm(tn, Wt[aname + ".proj_in.w"], C, 1, 1, M, hs, bias=Wt[aname + ".proj_in.b"])
+                stats = None
+            else:
+                # every GEMM that writes the residual stream ``hs`` also writes its per-row partial sums; the three
+                # LayerNorms of a block are folded into the GEMMs that consume them (no LN launches, no LN buffer)
+                parts = P.gemm_stats_parts(tn, Wt[aname + ".proj_in.w"], C, 1, 1, M, hs)
+                key = ("ln_stats", M, parts)
+                if key not in self._scratch:
+                    self._scratch[key] = torch.zeros(M, parts, 2, **f32)
+                stats = self._scratch[key]
+                P.gemm(tn, Wt[aname + ".proj_in.w"], C, 1, 1, M, hs, bias=Wt[aname + ".proj_in.b"], stats_out=stats)
+
+            def ln_of(t, key):
+                return dict(stats=stats, csum=Wt[t + key + ".csum"], bias=Wt[t + key + ".lnb"], eps=1e-5)
+
             for d in range(Wt[aname + ".depth"]):
                 t = f"{aname}.transformer_blocks.{d}"
-                ln = scratch("ln", M, C)
-                P.layernorm(hs, Wt[t + ".norm1.g"], Wt[t + ".norm1.b"], 1e-5, ln)
                 qkv = scratch("qkv", M, 3 * C)
-                P.gemm(ln, Wt[t + ".attn1.qkv.w"], 3 * C, 1, 1, M, qkv)
                 att = scratch("att", M, C)
-                P.attention(qkv, qkv, qkv, att, B, heads, S, S, 0, C, 2 * C, cfg.head_dim ** -0.5)
-                P.gemm(att, Wt[t + ".attn1.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".attn1.out.b"], res=hs)
-                P.layernorm(hs, Wt[t + ".norm2.g"], Wt[t + ".norm2.b"], 1e-5, ln)
                 q = scratch("q", M, C)
-                P.gemm(ln, Wt[t + ".attn2.q.w"], C, 1, 1, M, q)
+                gg = scratch("geglu", M, 4 * C)
                 kv = persist(B * 77, 2 * C)         # depends on the conditioning only: computed by prog_ctx
                 PC.gemm(self.ctx, Wt[t + ".attn2.kv.w"], 2 * C, 1, 1, B * 77, kv)
                 kv_cache[t] = kv
+                if fold:
+                    P.gemm(hs, Wt[t + ".attn1.qkv.w"], 3 * C, 1, 1, M, qkv, ln=ln_of(t, ".attn1.qkv"))
+                    P.attention(qkv, qkv, qkv, att, B, heads, S, S, 0, C, 2 * C, cfg.head_dim ** -0.5)
+                    P.gemm(att, Wt[t + ".attn1.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".attn1.out.b"], res=hs, stats_out=stats)
+                    P.gemm(hs, Wt[t + ".attn2.q.w"], C, 1, 1, M, q, ln=ln_of(t, ".attn2.q"))
+                    P.attention(q, kv, kv, att, B, heads, S, 77, 0, 0, C, cfg.head_dim ** -0.5)
+                    P.gemm(att, Wt[t + ".attn2.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".attn2.out.b"], res=hs, stats_out=stats)
+                    P.gemm(hs, Wt[t + ".ff.in.w"], 8 * C, 1, 1, M, gg, mode=1, ln=ln_of(t, ".ff.in"))
+                    P.gemm(gg, Wt[t + ".ff.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".ff.out.b"], res=hs, stats_out=stats)
+                    continue
+                ln = scratch("ln", M, C)
+                P.layernorm(hs, Wt[t + ".norm1.g"], Wt[t + ".norm1.b"], 1e-5, ln)
+                P.gemm(ln, Wt[t + ".attn1.qkv.w"], 3 * C, 1, 1, M, qkv)
+                P.attention(qkv, qkv, qkv, att, B, heads, S, S, 0, C, 2 * C, cfg.head_dim ** -0.5)
+                P.gemm(att, Wt[t + ".attn1.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".attn1.out.b"], res=hs)
+                P.layernorm(hs, Wt[t + ".norm2.g"], Wt[t + ".norm2.b"], 1e-5, ln)
+                P.gemm(ln, Wt[t + ".attn2.q.w"], C, 1, 1, M, q)
                 P.attention(q, kv, kv, att, B, heads, S, 77, 0, 0, C, cfg.head_dim ** -0.5)
                 P.gemm(att, Wt[t + ".attn2.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".attn2.out.b"], res=hs)
                 P.layernorm(hs, Wt[t + ".norm3.g"], Wt[t + ".norm3.b"], 1e-5, ln)
-                gg = scratch("geglu", M, 4 * C)
                 P.gemm(ln, Wt[t + ".ff.in.w"], 8 * C, 1, 1, M, gg, bias=Wt[t + ".ff.in.b"], mode=1)
                 P.gemm(gg, Wt[t + ".ff.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".ff.out.b"], res=hs)
             P.gemm(hs, Wt[aname + ".proj_out.w"], C, 1, 1, M, out, bias=Wt[aname + ".proj_out.b"], res=x)

@@ -5,11 +5,8 @@ interpolate_spherical  <- utils.py:29-71   (K1 kernel, lb_slerp_rows)
 interpolate_linear     <- utils.py:74-102  (lb_lerp for CUDA tensors; numpy for
                                             uint8 frames, which never touch the GPU)
 """
-import time
-
 import numpy as np
 import torch
-import yaml
 
 from . import ops
 
@@ -39,22 +36,12 @@ def interpolate_linear(p0, p1, fract_mixing):
     return np.clip(out, 0, 255).astype(np.uint8) if back else out
 
 
-def add_frames_linear_interp(list_imgs, fps_target=None, duration_target=None, nmb_frames_target=None, seed=None):
-    """Fill a frame list up to an exact frame count with linear blends
-    (utils.py:105-178).  The per-gap insert counts are drawn at random until they
-    sum to the target; ``seed`` makes that reproducible."""
-    if nmb_frames_target is not None and fps_target is not None:
-        raise ValueError("You cannot specify both fps_target and nmb_frames_target")
-    if fps_target is None:
-        assert nmb_frames_target is not None, "Either specify nmb_frames_target or fps_target+duration_target"
-    if nmb_frames_target is None:
-        assert fps_target is not None and duration_target is not None
-        nmb_frames_target = fps_target * duration_target
-    gaps = len(list_imgs) - 1
+def _insert_counts(gaps, nmb_frames_target, seed=None):
+    """Frames to insert into each gap so the total is exactly ``nmb_frames_target`` (utils.py:143-160: floor of the
+    mean plus a random 0/1 per gap, redrawn until the sum fits).  None when nothing is missing."""
     missing = nmb_frames_target - gaps - 1
     if missing < 1:
-        return list_imgs
-    frames = [np.asarray(im).astype(np.float32) for im in list_imgs]
+        return None
     mean_ins = missing / gaps
     base = np.floor(mean_ins)
     thresh = 1 - (mean_ins - base)
@@ -63,45 +50,50 @@ def add_frames_linear_interp(list_imgs, fps_target=None, duration_target=None, n
         ins = (rng.rand(gaps) > thresh).astype(np.float64) + base
         if np.sum(ins) == missing:
             break
-    ins = ins.astype(np.int32)
+    return ins.astype(np.int32)
+
+
+def plan_frame_fill(n_key_frames, nmb_frames_target, seed=None):
+    """The frame fill of add_frames_linear_interp as index/weight arrays for lb_frames_lerp_u8: output frame t is
+    uint8(float32(w0[t]) * key[left[t]] + float32(w1[t]) * key[left[t]+1]) -- numpy's float32 blend
+    ``(1 - f) * img0 + f * img1`` (utils.py:97,170) of the reference's float32 images."""
+    gaps = n_key_frames - 1
+    ins = _insert_counts(gaps, nmb_frames_target, seed)
+    if ins is None:
+        ins = np.zeros(gaps, dtype=np.int32)
+    left, w0, w1 = [], [], []
+    for i in range(gaps):
+        left.append(i); w0.append(1.0); w1.append(0.0)
+        for f in np.linspace(0, 1, ins[i] + 2)[1:-1]:
+            left.append(i); w0.append(1 - f); w1.append(f)
+    left.append(gaps - 1 if gaps > 0 else 0); w0.append(0.0 if gaps > 0 else 1.0); w1.append(1.0 if gaps > 0 else 0.0)
+    return (np.asarray(left, dtype=np.int32), np.asarray(w0, dtype=np.float64).astype(np.float32),
+            np.asarray(w1, dtype=np.float64).astype(np.float32))
+
+
+def add_frames_linear_interp(list_imgs, fps_target=None, duration_target=None, nmb_frames_target=None, seed=None):
+    """Fill a frame list up to an exact frame count with linear blends
+    (utils.py:105-178).  The per-gap insert counts are drawn at random until they
+    sum to the target; ``seed`` makes that reproducible.  Host (numpy) version for images that are not on the
+    device; BlendingEngine.get_movie_frames runs the same plan through lb_frames_lerp_u8."""
+    if nmb_frames_target is not None and fps_target is not None:
+        raise ValueError("You cannot specify both fps_target and nmb_frames_target")
+    if fps_target is None:
+        assert nmb_frames_target is not None, "Either specify nmb_frames_target or fps_target+duration_target"
+    if nmb_frames_target is None:
+        assert fps_target is not None and duration_target is not None
+        nmb_frames_target = fps_target * duration_target
+    gaps = len(list_imgs) - 1
+    ins = _insert_counts(gaps, nmb_frames_target, seed)
+    if ins is None:
+        return list_imgs
+    frames = [np.asarray(im).astype(np.float32) for im in list_imgs]
     out = []
     for i in range(gaps):
         out.append(frames[i].astype(np.uint8))
         for f in np.linspace(0, 1, ins[i] + 2)[1:-1]:
-            out.append(interpolate_linear(frames[i], frames[i + 1], f).astype(np.uint8))
+            # float32 arithmetic like the reference's numpy (value-based casting of the float64 scalar)
+            blend = np.float32(1 - f) * frames[i] + np.float32(f) * frames[i + 1]
+            out.append(blend.astype(np.uint8))
     out.append(frames[-1].astype(np.uint8))
     return out
-
-
-def get_spacing(nmb_points: int, scaling: float):
-    """Non-linear spacing on [0,1], denser around 0.5 (utils.py:181-200)."""
-    if scaling < 1.7:
-        return np.linspace(0, 1, nmb_points)
-    per_side = nmb_points // 2 + 1
-    left = np.abs(np.linspace(1, 0, per_side) ** scaling / 2 - 0.5)
-    if nmb_points % 2 != 0:
-        right = 1 - left[::-1][1:]
-    else:
-        left = left[:-1]
-        right = 1 - left[::-1]
-    return np.hstack([left, right])
-
-
-def get_time(resolution=None):
-    """Time string like 221117_1620 (utils.py:203-221)."""
-    fmt = {None: "%y%m%d_%H%M%S", "second": "%y%m%d_%H%M%S", "minute": "%y%m%d_%H%M", "day": "%y%m%d"}
-    if resolution == "millisecond":
-        return time.strftime("%y%m%d_%H%M%S", time.localtime()) + "_{:03d}".format(int((time.time() % 1) * 1000))
-    if resolution not in fmt:
-        raise ValueError("bad resolution provided: %s" % resolution)
-    return time.strftime(fmt[resolution], time.localtime())
-
-
-def yml_load(fp_yml, print_fields=False):
-    with open(fp_yml) as f:
-        return dict(yaml.load(f, Loader=yaml.loader.SafeLoader))
-
-
-def yml_save(fp_yml, dict_stuff):
-    with open(fp_yml, "w") as f:
-        yaml.dump(dict_stuff, f, sort_keys=False, default_flow_style=False)

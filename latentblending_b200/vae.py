@@ -73,6 +73,8 @@ class VAEDecoderB200:
         W["conv_out.w"] = g("conv_out.weight").permute(0, 2, 3, 1).contiguous()
         W["conv_out.b"] = g("conv_out.bias")
         self._plans = {}
+        self.nonfinite = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.decodes_since_check = 0
 
     def plan(self, h, w):
         if (h, w) not in self._plans:
@@ -87,7 +89,26 @@ class VAEDecoderB200:
         pl = self.plan(h, w)
         pl.z_in.copy_(latents)
         pl.prog.run()
+        self.decodes_since_check += 1
         return pl.frame.clone()
+
+    def overflow_count(self):
+        """Non-finite pixels seen by the post-process kernel since the last call (device->host read: call it at a
+        point that synchronises anyway).  The decoder stores fp16 where the reference upcasts the stock SDXL VAE to
+        fp32 (diffusers_holder.py:128-133); with weights that overflow fp16 this is > 0 and the frames are invalid."""
+        n = int(self.nonfinite.item())
+        if n:
+            self.nonfinite.zero_()
+        self.decodes_since_check = 0
+        return n
+
+    def check_overflow(self):
+        n = self.overflow_count()
+        if n:
+            raise _cabi.LB200Error(
+                f"VAE decode produced {n} non-finite pixels: these VAE weights overflow fp16 (the reference upcasts the "
+                "stock SDXL VAE to fp32, diffusers_holder.py:128-133); use the fp16-safe SDXL VAE weights "
+                "(madebyollin/sdxl-vae-fp16-fix) with this backend")
 
 
 class _VAELowering:
@@ -166,6 +187,6 @@ class _VAELowering:
         P.groupnorm(x, B, hh * ww, cin, groups, Wt["norm_out.g"], Wt["norm_out.b"], 1e-6, 1, no, self.ws)
         img = torch.empty(1, 3, hh, ww, **f16)
         P.conv_out(no, B, hh, ww, cin, Wt["conv_out.w"], Wt["conv_out.b"], 3, img)
-        P.postprocess_u8(img, self.frame)
+        P.postprocess_u8(img, self.frame, vae.nonfinite)
         self._keep = (scratch, z, qk, vT, scores, x2, x3, x4, img)
         P.finalize()

@@ -33,7 +33,7 @@ def test_ctypes_signatures_cover_header(lib_path):
     from latentblending_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == _declared()
     lib = _cabi.load()
-    assert lib.lb_abi_version() == 1
+    assert lib.lb_abi_version() == 2
 
 
 def test_product_never_imports_oracle():

@@ -36,13 +36,26 @@ def sim(a, b):
     return float((a.float() - b.float()).abs().mean() / 255.0)
 
 
-def make_compute(tree, N):
-    def compute(fract, p1, p2, idx):
+def make_compute(tree, N, log=None):
+    def compute(fract, p1, p2, idx, cfg_split=None):
+        """cfg_split mimics the CFG pair: each member computes HALF of the per-step update (its "eps half") and the
+        halves are exchanged inside the 2-rank team group every step, like DiffusersHolder.cfg_split."""
         f = (fract - tree.tree_fracts[p1]) / (tree.tree_fracts[p2] - tree.tree_fracts[p1])
         traj = [None] * N
         lat = ((1 - f) * tree.tree_latents[p1][idx - 1].float() + f * tree.tree_latents[p2][idx - 1].float()).half()
+        if log is not None:
+            log.append((fract, None if cfg_split is None else cfg_split["half"]))
         for i in range(idx, N):
-            lat = (lat.float() * 0.9 + 0.1 * torch.sin(3 * lat.float() + i + 10 * fract)).half()
+            upd = 0.1 * torch.sin(3 * lat.float() + i + 10 * fract)
+            if cfg_split is not None:
+                half = upd.clone()
+                flat = half.view(-1)
+                n2 = flat.numel() // 2
+                mine = flat[:n2].clone() if cfg_split["half"] == 0 else flat[n2:].clone()
+                parts = [torch.empty_like(mine), torch.empty_like(mine)]
+                dist.all_gather(parts, mine, group=cfg_split["group"])
+                upd = torch.cat(parts).view(upd.shape)
+            lat = (lat.float() * 0.9 + upd).half()
             traj[i] = lat.clone()
         return traj, frame_of(traj[-1])
     return compute
@@ -51,6 +64,7 @@ def make_compute(tree, N):
 def sequential(N, levels, seed):
     """The reference's loop (blending_engine.py:354-362, :531-588) in one process."""
     tree = Tree(N, seed)
+    tree.insert_order = []
     compute = make_compute(tree, N)
     for idx, stems in levels:
         for _ in range(stems):
@@ -64,6 +78,7 @@ def sequential(N, levels, seed):
                 p2 += 1
             assert (p1, p2) == older_parents(tree.tree_fracts, tree.tree_idx_injection, mid, idx)
             traj, frm = compute(mid, p1, p2, idx)
+            tree.insert_order.append(mid)
             left, right = sim(frm, tree.frames[c1]), sim(frm, tree.frames[c1 + 1])
             k = c1 + 1
             tree.tree_latents.insert(k, traj)
@@ -75,17 +90,19 @@ def sequential(N, levels, seed):
     return tree
 
 
-def _worker(rank, world, port, N, levels, seed, q):
+def _worker(rank, world, port, N, levels, seed, q, pairs=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     tree = Tree(N, seed)
-    sh = LevelSharder(rank, world)
-    compute = make_compute(tree, N)
+    sh = LevelSharder(rank, world, cfg_pairs=pairs)
+    log, inserted = [], []
+    compute = make_compute(tree, N, log)
     for idx, stems in levels:
-        sh.run_level(tree, idx, stems, compute, (lambda a, b: sim(a, b) if rank == 0 else 0.0), N)
+        # every rank evaluates the similarities itself (deterministic) -- no broadcast from rank 0
+        sh.run_level(tree, idx, stems, compute, sim, N, on_insert=inserted.append)
     q.put((rank, tree.tree_fracts, tree.tree_idx_injection, tree.tree_similarities,
-           [float(t[-1].float().sum()) for t in tree.tree_latents], sh.stats))
+           [float(t[-1].float().sum()) for t in tree.tree_latents], sh.stats, inserted, log))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -98,29 +115,40 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,levels", [(2, [(15, 4), (18, 3), (21, 3), (24, 2), (27, 1)]),
-                                          (3, [(2, 7)]), (2, [(10, 1), (20, 6)])])
-def test_sharded_tree_equals_sequential(world, levels):
+@pytest.mark.parametrize("world,levels,pairs", [(2, [(15, 4), (18, 3), (21, 3), (24, 2), (27, 1)], False),
+                                                (3, [(2, 7)], False), (2, [(10, 1), (20, 6)], False),
+                                                (2, [(15, 4), (18, 3), (27, 1)], True),
+                                                (4, [(15, 4), (18, 3), (21, 3), (24, 2), (27, 1)], True)])
+def test_sharded_tree_equals_sequential(world, levels, pairs):
     N, seed = 30, 7
     ref = sequential(N, levels, seed)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, N, levels, seed, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, levels, seed, q, pairs)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, fracts, idxs, sims, sums, stats in results:
+    for rank, fracts, idxs, sims, sums, stats, inserted, log in results:
         assert fracts == ref.tree_fracts, rank
         assert idxs == ref.tree_idx_injection
         np.testing.assert_allclose(sims, ref.tree_similarities, rtol=0, atol=0)
         assert sums == [float(t[-1].float().sum()) for t in ref.tree_latents]
         assert stats["used"] == sum(s for _, s in levels)
+        # on_insert ran on EVERY rank once per inserted branch, in the sequential insertion order
+        assert inserted == ref.insert_order, rank
+        if pairs:
+            assert stats["paired_rounds"] >= 1
+            assert any(h == rank % 2 for _, h in log if h is not None) or world == 3
+        else:
+            assert all(h is None for _, h in log)
     # speculation can only save rounds, never add any
     assert results[0][5]["rounds"] <= sum(s for _, s in levels)
+    if pairs and world == 4:
+        assert results[0][5]["paired_rounds"] == results[0][5]["rounds"]      # 4 ranks: always two teams of two
     print("rounds", results[0][5]["rounds"], "of", sum(s for _, s in levels), "branches; computed",
           results[0][5]["computed"])
 

@@ -1,7 +1,10 @@
 """GPU parity of the lowered UNet program (liblb200) against the CPU oracle UNet
 (oracle/sdxl_unet.py, fp32) on identical seeded weights and inputs.
 Tolerance (stated): relative L2 error of eps <= 5e-3 -- fp16 storage of every
-activation with fp32 accumulation vs an all-fp32 oracle."""
+activation with fp32 accumulation vs an all-fp32 oracle.  At the BENCHMARKED shape
+(full SDXL-base, CFG batch 2, 128x128 latents) the comparison is against the committed
+fixture tests/golden/unet_sdxl_b2_128.npz (tests/golden/make_fullsize_fixtures.py).
+Measured rel-L2 values are printed (-s) and recorded in DESIGN.md section 5."""
 import dataclasses
 
 import pytest
@@ -63,11 +66,66 @@ def test_medium_unet_matches_oracle():
     assert rel <= 5e-3, f"relative L2 error {rel}"
 
 
+_FULL = {}
+
+
+def _full_sdxl():
+    """The seeded full-size oracle UNet (2.57 B parameters, ~1 min of CPU init) and its CUDA twin, built once."""
+    if not _FULL:
+        from latentblending_b200.unet import UNetB200, UNetConfig
+        from make_fullsize_fixtures import oracle_unet, weights_checksum
+        from oracle.sdxl_unet import SDXL_BASE
+        oracle = oracle_unet()
+        cfg = UNetConfig(**{f.name: getattr(SDXL_BASE, f.name) for f in dataclasses.fields(SDXL_BASE)})
+        _FULL.update(oracle=oracle, net=UNetB200(cfg, oracle.state_dict(), "cuda:0"),
+                     sha=weights_checksum(oracle.state_dict()))
+    return _FULL
+
+
 @pytest.mark.slow
 def test_full_sdxl_unet_matches_oracle_at_256px():
     """The real SDXL-base architecture (2.57 B parameters), 32x32 latents, CFG batch 2."""
+    from latentblending_b200 import ops
     from oracle.sdxl_unet import SDXL_BASE
-    rel, eps, ref, net = _run_pair(SDXL_BASE, 2, 32, 32, 925.0)
+    full = _full_sdxl()
+    x, ctx, pooled, tids = _inputs(SDXL_BASE, 2, 32, 32, 0)
+    with torch.no_grad():
+        ref = full["oracle"](x.float(), 925.0, ctx.float(), pooled.float(), tids.float())
+    eps = full["net"].forward(x.cuda(), 925.0, ctx.cuda(), pooled.cuda(), tids.cuda()).float().cpu()
+    assert ops.error_flag() == 0
+    rel = ((eps - ref).norm() / ref.norm()).item()
+    print(f"full SDXL UNet @32x32 B=2: rel_l2={rel:.3e}")
     assert torch.isfinite(eps).all()
     assert rel <= 5e-3, f"relative L2 error {rel}"
-    assert net.launches_per_forward(2, 32, 32)[0] > 900
+    assert full["net"].launches_per_forward(2, 32, 32)[0] > 600
+
+
+@pytest.mark.slow
+def test_full_sdxl_unet_matches_fixture_at_bench_shape():
+    """Parity AT THE BENCHMARKED SHAPE: one CFG-batch-2 forward of the full SDXL-base UNet at 128x128 latents vs the
+    fp32 oracle output committed as a fixture (the oracle needs ~30 s x 8 cores for this forward; the GPU box only
+    rebuilds the seeded weights, whose checksum is verified first)."""
+    from latentblending_b200 import ops
+    from make_fullsize_fixtures import UNET_FIXTURE, UNET_SEED, UNET_T, unet_inputs
+    from oracle.sdxl_unet import SDXL_BASE
+    import numpy as np
+    fx = np.load(UNET_FIXTURE)
+    full = _full_sdxl()
+    assert full["sha"] == str(fx["weights_sha1"]), "seeded weight recipe drifted from the fixture's"
+    x, ctx, pooled, tids = unet_inputs(SDXL_BASE, 2, 128, 128, UNET_SEED)
+    eps = full["net"].forward(x.cuda(), float(fx["t"]), ctx.cuda(), pooled.cuda(), tids.cuda()).float().cpu()
+    torch.cuda.synchronize()
+    assert ops.error_flag() == 0
+    ref = torch.from_numpy(fx["eps"])
+    assert float(fx["t"]) == UNET_T and eps.shape == ref.shape == (2, 4, 128, 128)
+    rel = ((eps - ref).norm() / ref.norm()).item()
+    mse = ((eps - ref) ** 2).mean().item()
+    print(f"full SDXL UNet @128x128 B=2 (bench shape): rel_l2={rel:.3e} mse={mse:.3e} max={float((eps - ref).abs().max()):.3e}")
+    assert torch.isfinite(eps).all()
+    assert rel <= 5e-3, f"relative L2 error {rel}"
+    # batch invariance at the bench shape: each CFG half alone reproduces its half of the batch-2 forward bit for bit
+    # (what the multi-GPU CFG split and the lockstep batching rely on)
+    for b in range(2):
+        one = full["net"].forward(x[b:b + 1].cuda(), float(fx["t"]), ctx[b:b + 1].cuda(), pooled[b:b + 1].cuda(),
+                                  tids[b:b + 1].cuda()).float().cpu()
+        assert torch.equal(one[0], eps[b]), f"batch-1 forward of half {b} differs from the batch-2 forward"

@@ -29,3 +29,23 @@ def test_vae_decoder_matches_oracle(h, w):
     assert ref.std() > 5            # the frame is not degenerate
     from latentblending_b200 import ops
     assert ops.error_flag() == 0
+
+
+def test_sdxl_width_vae_matches_fixture():
+    """The SDXL-width decoder (128,256,512,512) at 64x64 latents vs the fp32 oracle frame committed as a fixture
+    (tests/golden/vae_sdxl_64.npz, tests/golden/make_fullsize_fixtures.py).  Same tolerance as above."""
+    from latentblending_b200 import ops
+    from latentblending_b200.vae import VAEDecoderB200
+    from make_fullsize_fixtures import VAE_FIXTURE, oracle_vae, vae_latent, weights_checksum
+    fx = np.load(VAE_FIXTURE)
+    ov, cfg = oracle_vae()
+    assert weights_checksum(ov.state_dict()) == str(fx["weights_sha1"]), "seeded VAE recipe drifted"
+    vae = VAEDecoderB200(ov.state_dict(), cfg.block_out_channels, cfg.scaling_factor, "cuda:0")
+    got = vae.decode_to_u8(vae_latent(64, 64).cuda()).cpu().numpy()
+    ref = fx["frame"]
+    assert got.shape == ref.shape == (512, 512, 3)
+    d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    print(f"SDXL-width VAE @64x64: mean |d|={d.mean():.3f} max={d.max()} levels")
+    assert d.mean() <= 1.0 and d.max() <= 12, (d.mean(), d.max())
+    assert ops.error_flag() == 0
+    assert vae.overflow_count() == 0
