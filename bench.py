@@ -482,7 +482,7 @@ def run_ours(args):
                     peak=peak_tf, unit="TFLOP/s", frac=gemm_tf / peak_tf, frac_of_burst_peak=gemm_tf / peak_burst,
                     traffic=tr.get("gemm", {}).get("dram_bytes_per_launch"),
                     traffic_source=tr.get("gemm", {}).get("source"),
-                    algorithmic_bytes_per_launch=tr.get("gemm", {}).get("algorithmic_bytes_per_launch"),
+                    algorithmic_bytes_per_launch=work["gemm_bytes"] / max(1, breakdown["gemm"]["launches"]),
                     peak_source=f"{pk['source']} bf16_tflops_sustained (the replay follows minutes of load under the "
                                 f"power cap; burst peak {peak_burst} also given)",
                     algorithmic_flops_per_unet_forward=work["gemm_flops"],

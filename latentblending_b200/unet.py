@@ -240,12 +240,17 @@ class Program:
         return int(_cabi.load().lb_program_count_kinds(self.handle, mask))
 
     def work(self):
-        """Algorithmic work of the recorded ops: {'gemm_flops', 'attn_flops', 'norm_bytes'}."""
-        gemm = attn = norm = 0
+        """Algorithmic work of the recorded ops: {'gemm_flops', 'gemm_bytes', 'attn_flops', 'norm_bytes'}.
+        gemm_bytes = fp16 bytes every GEMM must move at least once: A (M x C per input tensor -- a 3x3 conv reads its
+        activation once), W (N x K), the output and the residual."""
+        gemm = attn = norm = gbytes = 0
         for op in self.ops:
             if op.kind == OP_GEMM:
                 d = op.u.gemm
-                gemm += 2 * d.B * d.H * d.W * d.N * (d.taps * d.a0_c + (d.a1_c if d.a1 else 0))
+                M, K = d.B * d.H * d.W, d.taps * d.a0_c + (d.a1_c if d.a1 else 0)
+                gemm += 2 * M * d.N * K
+                n_out = d.N // 2 if (d.mode & 0xff) == 1 else d.N
+                gbytes += 2 * (M * (d.a0_c + (d.a1_c if d.a1 else 0)) + d.N * K + M * n_out + (M * d.N if d.res else 0))
             elif op.kind == OP_ATTENTION:
                 d = op.u.attn
                 attn += 4 * d.B * d.heads * d.Sq * d.Skv * d.head_dim
@@ -253,7 +258,7 @@ class Program:
                 d = op.u.norm
                 rows = d.rows * (d.B if op.kind == OP_GROUPNORM else 1)
                 norm += 4 * rows * d.C
-        return dict(gemm_flops=gemm, attn_flops=attn, norm_bytes=norm)
+        return dict(gemm_flops=gemm, gemm_bytes=gbytes, attn_flops=attn, norm_bytes=norm)
 
     def __del__(self):
         try:

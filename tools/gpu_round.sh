@@ -11,7 +11,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 for s in $SECTIONS; do
 case $s in
 tests)
-  ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $O/pytest.log 2>&1; echo "pytest exit $?"; tail -5 $O/pytest.log ;;
+  ( time timeout 1500 python -m pytest tests -m gpu -q -s ) > $O/pytest.log 2>&1; echo "pytest exit $?"; grep -E "passed|failed|error" $O/pytest.log | tail -5; grep -E "^(FAILED|ERROR)" $O/pytest.log | head -30 ;;
 smoke)
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke exit $?"; tail -3 $O/smoke.log ;;
 optests)
@@ -27,12 +27,29 @@ ops)
   timeout 300 python tools/bench_ops.py attn gemm > $O/bench_ops.txt 2>&1; cat $O/bench_ops.txt
   timeout 300 python tools/bench_mix.py > $O/bench_mix.txt 2>&1; cat $O/bench_mix.txt ;;
 bench)
-  timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/bench.json 2> $O/bench.err; echo "bench exit $?"; cat $O/bench.json; tail -3 $O/bench.err ;;
+  timeout 1200 python bench.py --steps 2 --warmup 2 ${BENCH_ARGS:-} > $O/bench.json 2> $O/bench.err; echo "bench exit $?"; cat $O/bench.json; tail -3 $O/bench.err ;;
 parts)
   timeout 600 python tools/time_parts.py > $O/time_parts.txt 2>&1; head -12 $O/time_parts.txt ;;
 launches)
   timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
      --log-file $O/unet_launches.csv python tools/profile_unet.py > $O/unet_launches.log 2>&1; echo "launches exit $?" ;;
+traffic)
+  timeout 900 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
+     --clock-control none --csv --log-file $O/unet_traffic.csv python tools/profile_unet.py > $O/unet_traffic.log 2>&1; echo "traffic exit $?"
+  timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
+     -k regex:slerp_l2 -s 5 -c 2 --log-file $O/mix_traffic.csv python tools/bench_mix.py > $O/mix_traffic.log 2>&1; echo "mix traffic exit $?" ;;
+small)
+  timeout 300 python tools/bench_small.py > $O/bench_small.txt 2>&1; cat $O/bench_small.txt ;;
+ncu_small)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gn_|ln_kernel|cfg_euler|scale_input|embed_inputs" -c 24 -o $O/small -f \
+     env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_small.py > $O/ncu_small.log 2>&1; echo "ncu small exit $?" ;;
+cluster2)
+  LB_GEMM_CLUSTER=2 timeout 300 python tools/bench_ops.py gemm > $O/bench_ops_cluster2.txt 2>&1; cat $O/bench_ops_cluster2.txt ;;
+lnfold)
+  timeout 300 python tools/time_unet_batch.py > $O/unet_batch_lnfold.txt 2>&1; cat $O/unet_batch_lnfold.txt
+  LB_NO_LN_FOLD=1 timeout 300 python tools/time_unet_batch.py > $O/unet_batch_nofold.txt 2>&1; cat $O/unet_batch_nofold.txt ;;
+refarm)
+  ( time timeout 900 python bench.py --impl reference --steps 2 --warmup 1 ) > $O/bench_ref.json 2> $O/bench_ref.err; echo "ref exit $?"; cat $O/bench_ref.json; tail -4 $O/bench_ref.err ;;
 ncu)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_tc -c 5 -o $O/attn -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_ops.py attn > $O/ncu_attn.log 2>&1; echo "ncu attn exit $?"
