@@ -72,6 +72,7 @@ class BlendingEngine():
         self.lpips = None
         self._pending_timing = None
         if similarity_fn is None:
+            pipe = getattr(self.dh, "pipe", pipe)       # the adapted pipe (a diffusers pipeline is wrapped by the holder)
             sd = getattr(pipe, "lpips_state_dict", None)
             if sd is None:
                 # Random AlexNet weights only RANK gaps of a synthetic pipe; with real UNet / VAE weights they would

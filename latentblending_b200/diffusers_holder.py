@@ -30,6 +30,8 @@ class DiffusersHolder:
         self.negative_prompt = ""                 # reference defaults, diffusers_holder.py:23-25
         self.guidance_scale = 5.0
         self.num_inference_steps = 30
+        from .pipe import adapt_pipe
+        pipe = adapt_pipe(pipe)               # a diffusers StableDiffusionXLPipeline is wrapped (reference contract)
         self.pipe = pipe
         self.device = str(pipe._execution_device)
         if not torch.cuda.is_available() or not self.device.startswith("cuda"):

@@ -178,6 +178,7 @@ def prompt_seed(prompt: str) -> int:
 
 class SyntheticSDXLPipe:
     vae_scale_factor = 8
+    is_synthetic = True       # seeded random weights / embeddings: BlendingEngine may fall back to seeded LPIPS weights
 
     def __init__(self, name="stabilityai/stable-diffusion-xl-base-1.0", device="cuda:0", unet_cfg: UNetConfig = None,
                  seed=0, unet_state_dict=None, vae_state_dict=None, vae_channels=VAE_CHANNELS,
@@ -216,3 +217,101 @@ class SyntheticSDXLPipe:
         neg = negative_prompt[0] if isinstance(negative_prompt, (list, tuple)) else (negative_prompt or "")
         ne, npool = emb("<neg>" + neg)
         return pe, ne, pp, npool
+
+
+class DiffusersSDXLPipe:
+    """Adapter: a loaded diffusers ``StableDiffusionXLPipeline`` (what the reference's constructor receives,
+    latentblending/blending_engine.py:20-44 via AutoPipelineForText2Image) -> the attribute surface
+    ``DiffusersHolder`` of this backend reads.  ``BlendingEngine(pipe)`` / ``DiffusersHolder(pipe)`` wrap a real
+    pipeline automatically (``adapt_pipe``), so the reference's call
+
+        pipe = AutoPipelineForText2Image.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", torch_dtype=torch.float16, variant="fp16")
+        pipe.to("cuda"); be = BlendingEngine(pipe)
+
+    keeps working.  What is taken from the pipeline: the UNet / VAE-decoder ``state_dict()`` (diffusers parameter names
+    are the ones the packers use), the UNet config, the scheduler config (EulerTables), ``encode_prompt`` (the CLIP text
+    encoders stay PyTorch modules: they run once per prompt and are outside the hot path) and
+    ``_execution_device`` / ``_name_or_path`` / ``default_sample_size`` / ``vae_scale_factor``.
+    ``lpips_state_dict`` must be supplied (see INTEGRATION.md "LPIPS weights"): with real weights a random LPIPS
+    network would silently steer the branch placement."""
+    is_synthetic = False
+
+    def __init__(self, pipe, lpips_state_dict=None):
+        from .schedulers import tables_from_diffusers_scheduler
+        self.inner = pipe
+        self._name_or_path = getattr(pipe, "_name_or_path", None) or pipe.config.get("_name_or_path", "")
+        self._execution_device = torch.device(pipe._execution_device)
+        self.device = self._execution_device
+        ucfg = pipe.unet.config
+
+        def get(k, default=None):
+            return ucfg[k] if k in ucfg else getattr(ucfg, k, default)
+        tl = get("transformer_layers_per_block", 1)
+        down = list(get("down_block_types"))
+        boc = tuple(get("block_out_channels"))
+        if isinstance(tl, int):
+            tl = [tl] * len(boc)
+        tl = tuple(int(t) if "CrossAttn" in d else 0 for t, d in zip(tl, down))
+        ahd = get("attention_head_dim")
+        heads = ahd if isinstance(ahd, (list, tuple)) else [ahd] * len(boc)
+        # SDXL's config stores the number of heads per level in attention_head_dim (5, 10, 20): head dim = C / heads
+        head_dims = {c // h for c, h, t in zip(boc, heads, tl) if t}
+        if head_dims != {64}:
+            raise ValueError(f"this backend implements head dim 64 (SDXL); the pipeline's UNet has {sorted(head_dims)}")
+        if get("addition_embed_type") != "text_time" or not get("use_linear_projection", False):
+            raise ValueError("not an SDXL UNet (needs addition_embed_type='text_time', use_linear_projection=True)")
+        pooled = int(get("projection_class_embeddings_input_dim")) - 6 * int(get("addition_time_embed_dim"))
+        self.unet_cfg = UNetConfig(in_channels=get("in_channels"), out_channels=get("out_channels"),
+                                   block_out_channels=boc, layers_per_block=get("layers_per_block"),
+                                   transformer_layers=tl, head_dim=64, cross_attention_dim=get("cross_attention_dim"),
+                                   addition_time_embed_dim=get("addition_time_embed_dim"), pooled_dim=pooled,
+                                   norm_num_groups=get("norm_num_groups"), sample_size=get("sample_size"),
+                                   time_cond_proj_dim=get("time_cond_proj_dim"))
+        self.default_sample_size = getattr(pipe, "default_sample_size", self.unet_cfg.sample_size)
+        self.vae_scale_factor = pipe.vae_scale_factor
+        self.scheduler = tables_from_diffusers_scheduler(pipe.scheduler)
+        self.unet_state_dict = pipe.unet.state_dict()
+        vsd = pipe.vae.state_dict()
+        self.vae_state_dict = OrderedDict((k[len("decoder."):] if k.startswith("decoder.") else k, v)
+                                          for k, v in vsd.items() if k.startswith(("decoder.", "post_quant_conv.")))
+        vcfg = pipe.vae.config
+        self.vae_channels = tuple(vcfg["block_out_channels"] if "block_out_channels" in vcfg else vcfg.block_out_channels)
+        self.vae_scaling_factor = float(vcfg["scaling_factor"] if "scaling_factor" in vcfg else vcfg.scaling_factor)
+        self.lpips_state_dict = lpips_state_dict if lpips_state_dict is not None else getattr(pipe, "lpips_state_dict", None)
+        self.h2d_bytes = 0
+
+    def encode_prompt(self, prompt, negative_prompt=None, do_classifier_free_guidance=True, dtype=torch.float16):
+        """diffusers_holder.py:79-96: the pipeline's own encode_prompt (both CLIP encoders), 4-tuple out."""
+        pe, ne, pp, npool = self.inner.encode_prompt(
+            prompt=prompt, prompt_2=prompt, device=self._execution_device, num_images_per_prompt=1,
+            do_classifier_free_guidance=do_classifier_free_guidance, negative_prompt=negative_prompt,
+            negative_prompt_2=negative_prompt)
+
+        def cvt(t):
+            return None if t is None else t.to(device=self._execution_device, dtype=dtype).contiguous()
+        return cvt(pe), cvt(ne), cvt(pp), cvt(npool)
+
+
+def adapt_pipe(pipe):
+    """What DiffusersHolder is built on: our own pipe objects pass through, a diffusers pipeline is wrapped."""
+    if hasattr(pipe, "unet_cfg") and hasattr(pipe, "unet_state_dict"):
+        return pipe
+    if hasattr(pipe, "unet") and hasattr(pipe, "vae") and hasattr(pipe, "encode_prompt"):
+        return DiffusersSDXLPipe(pipe)
+    raise TypeError("pipe must be a latentblending_b200 pipe (SyntheticSDXLPipe / DiffusersSDXLPipe) or a diffusers "
+                    "StableDiffusionXLPipeline")
+
+
+def lpips_state_dict_from_lpips(lpips_module):
+    """{convs.i.weight/bias, lins.i.weight} from an ``lpips.LPIPS(net='alex')`` instance (lpips==0.1.4 layout:
+    ``net.slice{1..5}`` hold AlexNet features 0,3,6,8,10; ``lin{0..4}.model[-1]`` the 1x1 weights)."""
+    sd = lpips_module.state_dict()
+    feats = (0, 3, 6, 8, 10)
+    out = {}
+    for i, f in enumerate(feats):
+        wk = next(k for k in sd if k.endswith(f".{f}.weight") and k.startswith("net."))
+        out[f"convs.{i}.weight"] = sd[wk]
+        out[f"convs.{i}.bias"] = sd[wk[:-len("weight")] + "bias"]
+        lk = next(k for k in sd if k.startswith(f"lin{i}.") and k.endswith("weight"))
+        out[f"lins.{i}.weight"] = sd[lk]
+    return out

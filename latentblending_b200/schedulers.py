@@ -29,7 +29,8 @@ def _h(x):
 class EulerTables:
     """kind: 'euler' (SDXL base) or 'euler_ancestral' (SDXL-Turbo)."""
 
-    def __init__(self, kind="euler", timestep_spacing=None, steps_offset=None, num_train_timesteps=1000):
+    def __init__(self, kind="euler", timestep_spacing=None, steps_offset=None, num_train_timesteps=1000,
+                 beta_start=0.00085, beta_end=0.012):
         assert kind in ("euler", "euler_ancestral")
         self.kind = kind
         self.ancestral = kind == "euler_ancestral"
@@ -37,7 +38,7 @@ class EulerTables:
         self.steps_offset = (0 if self.ancestral else 1) if steps_offset is None else steps_offset
         self.T = num_train_timesteps
         self.order = 1
-        self._train = _train_sigmas(num_train_timesteps)
+        self._train = _train_sigmas(num_train_timesteps, beta_start, beta_end)
         self.num_inference_steps = None
 
     def set_timesteps(self, n, device=None):
@@ -75,3 +76,25 @@ class EulerTables:
         if self.timestep_spacing in ("linspace", "trailing"):
             return smax
         return (smax ** 2 + 1) ** 0.5
+
+
+def tables_from_diffusers_scheduler(scheduler):
+    """EulerTables for a diffusers EulerDiscreteScheduler / EulerAncestralDiscreteScheduler instance (what
+    AutoPipelineForText2Image loads for SDXL base / SDXL-Turbo), from its ``config``.  Other scheduler classes,
+    beta schedules or prediction types are outside the reference's path (diffusers_holder.py:42,330,356) and raise."""
+    cfg = scheduler.config
+    name = type(scheduler).__name__
+    kinds = {"EulerDiscreteScheduler": "euler", "EulerAncestralDiscreteScheduler": "euler_ancestral"}
+    if name not in kinds:
+        raise ValueError(f"unsupported scheduler {name}: the latentblending path uses the Euler / Euler-ancestral "
+                         "schedulers SDXL base / SDXL-Turbo ship with")
+
+    def get(k, default=None):
+        return cfg[k] if k in cfg else getattr(cfg, k, default)
+    if get("beta_schedule", "scaled_linear") != "scaled_linear" or get("prediction_type", "epsilon") != "epsilon":
+        raise ValueError("only beta_schedule='scaled_linear' with prediction_type='epsilon' is implemented")
+    if get("use_karras_sigmas", False) or get("interpolation_type", "linear") != "linear":
+        raise ValueError("karras sigmas / log-linear interpolation are not implemented")
+    return EulerTables(kinds[name], timestep_spacing=get("timestep_spacing"), steps_offset=get("steps_offset", 0),
+                       num_train_timesteps=get("num_train_timesteps", 1000), beta_start=get("beta_start", 0.00085),
+                       beta_end=get("beta_end", 0.012))
