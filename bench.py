@@ -363,6 +363,10 @@ def run_ours(args):
     name = "stabilityai/sdxl-turbo" if cfg["model"] == "turbo" else "stabilityai/stable-diffusion-xl-base-1.0"
     pipe = SyntheticSDXLPipe(name, dev, seed=0)
     be = BlendingEngine(pipe)
+    if cfg["model"] == "turbo":
+        # ancestral noise per (seeds, branch position, step) instead of global-RNG draws: the tree then does not depend on
+        # the order branches are computed in (lockstep speculation, sharding), so fingerprints compare across --gpus
+        be.deterministic_noise = True
     be.set_negative_prompt(NEG)
     be.set_prompt1(PROMPTS[0])
     be.set_prompt2(PROMPTS[1])
@@ -505,6 +509,9 @@ def run_ours(args):
     par = "single GPU" if world == 1 else f"branch-sharded x{world} (CFG halves split over GPU pairs when stems < ranks)"
     wc = workload_config(cfg, par)
     wc["stems"] = stems_run
+    wc["speculative_batch"] = be._speculation_width() if world == 1 else 1
+    if getattr(be, "spec_stats", None) and world == 1:
+        wc["speculation"] = dict(be.spec_stats)
     if args.config == 4:
         wc.update(frames=frames // max(1, args.steps), t_compute_max_allowed=args.t_compute,
                   dt_unet_step=round(float(be.dt_unet_step), 5), dt_vae=round(float(be.dt_vae), 5))

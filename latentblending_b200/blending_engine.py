@@ -68,6 +68,13 @@ class BlendingEngine():
         self._similarity_fn = similarity_fn
         self.output_device_frames = False     # True: run_transition returns uint8 device frames, no D2H / PIL
         self.batch_outer_pair = True          # the two outer trajectories share batch-4 UNet forwards (same results)
+        # single-GPU speculation width: candidate branches of a level advanced in lockstep through ONE batched UNet
+        # forward (sharding.run_level_local).  None = by model: SDXL-Turbo 512^2 (weight-bandwidth / launch bound,
+        # a batch-4 forward costs about one batch-1 forward) -> 4; SDXL base 1024^2 -> 1 (batch 4 costs 1.76x batch 2)
+        self.speculative_batch = None
+        # ancestral-scheduler noise per (seeds, branch position, step) from its own generator instead of the global
+        # RNG: results then do not depend on the order branches are computed in (speculation, multi-GPU sharding)
+        self.deterministic_noise = False
         self.d2h_bytes = 0                    # bytes copied device->host for returned frames (bench e2e)
         self.lpips = None
         self._pending_timing = None
@@ -229,15 +236,77 @@ class BlendingEngine():
         # matters for the first argmax, so a placeholder keeps the same behaviour
         self.tree_similarities = [None]
 
+        width = self._speculation_width()
+        self.spec_stats = dict(rounds=0, computed=0, used=0)
         for s_idx in range(len(self.list_idx_injection)):
             nmb_stems = int(self.list_nmb_stems[s_idx])
             idx_injection = int(self.list_idx_injection[s_idx])
+            if width > 1 and nmb_stems > 1:
+                from .sharding import run_level_local
+                run_level_local(self, idx_injection, nmb_stems, self._compute_candidates, self.get_lpips_similarity,
+                                width, on_insert=self.set_guidance_mid_dampening, stats=self.spec_stats)
+                continue
             for _ in range(nmb_stems):
                 fract_mixing, b_parent1, b_parent2 = self.get_mixing_parameters(idx_injection)
                 self.set_guidance_mid_dampening(fract_mixing)
                 list_latents = self.compute_latents_mix(fract_mixing, b_parent1, b_parent2, idx_injection)
                 self.insert_into_tree(fract_mixing, idx_injection, list_latents)
         return self._finish_transition()
+
+    def _speculation_width(self):
+        if self._similarity_fn is not None or not hasattr(self.dh, "run_diffusion_sd_xl_multi"):
+            return 1
+        if self.speculative_batch is not None:
+            return max(1, int(self.speculative_batch))
+        return 4 if self.dh.is_sdxl_turbo else 1
+
+    def _guidance_for(self, fract_mixing):
+        """set_guidance_mid_dampening's value without touching the engine / holder state."""
+        mid_factor = 1 - np.abs(fract_mixing - 0.5) / 0.5
+        return self.guidance_scale_base - (self.guidance_scale_base * (1 - self.guidance_scale_mid_damper) - 1) * mid_factor
+
+    def _parental_coeffs(self, idx_injection):
+        """blending_engine.py:452-457."""
+        N = self.num_inference_steps
+        idx_mixing_stop = int(round(N * self.parental_crossfeed_range))
+        mixing_coeffs = idx_injection * [self.parental_crossfeed_power]
+        nmb_mixing = idx_mixing_stop - idx_injection
+        if nmb_mixing > 0:
+            mixing_coeffs.extend(list(np.linspace(self.parental_crossfeed_power,
+                                                  self.parental_crossfeed_power * self.parental_crossfeed_decay,
+                                                  nmb_mixing)))
+        mixing_coeffs.extend((N - len(mixing_coeffs)) * [0])
+        return mixing_coeffs
+
+    def _compute_candidates(self, cands, idx_injection):
+        """compute_latents_mix for several candidate branches of one level in ONE lockstep batch."""
+        self.dh.set_num_inference_steps(self.num_inference_steps)
+        jobs = []
+        for fract, p1, p2 in cands:
+            f_par = (fract - self.tree_fracts[p1]) / (self.tree_fracts[p2] - self.tree_fracts[p1])
+            mix = self._parental_mix(self.tree_latents[p1], self.tree_latents[p2], f_par)
+            jobs.append(dict(text_embeddings=self.get_mixed_conditioning(fract)[0], latents_start=mix[idx_injection - 1],
+                             list_latents_mixing=mix, mixing_coeffs=self._parental_coeffs(idx_injection),
+                             guidance_scale=self._guidance_for(fract), noise_fn=self._noise_source(fract)))
+        trajs = self.dh.run_diffusion_sd_xl_multi(jobs, idx_start=idx_injection)
+        return [(t, self._decode_frame(t[-1])) for t in trajs]
+
+    def _noise_source(self, key):
+        """noise_fn(step, shape) of the branch at position ``key`` (None: the scheduler's default global-RNG draws)."""
+        if not self.deterministic_noise:
+            return None
+        sched = getattr(getattr(self.dh, "pipe", None), "scheduler", None)
+        if not getattr(sched, "ancestral", False):
+            return None
+        return lambda step, shape: self._noise_for(key, step, shape)
+
+    def _noise_for(self, key, step, shape):
+        """Ancestral noise of (branch position ``key``, step) from a generator seeded by (seed1, seed2, key, step)."""
+        import struct
+        import zlib
+        seed = zlib.crc32(struct.pack("<qqdq", int(self.seed1), int(self.seed2), float(key), int(step))) & 0x7FFFFFFF
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        return torch.randn(shape, generator=g, device=self.device, dtype=torch.float16)
 
     def _finish_transition(self):
         if hasattr(self.dh, "check_decode_overflow"):
@@ -346,7 +415,7 @@ class BlendingEngine():
         list_conditionings = self.get_mixed_conditioning(0)
         ev0, ev1 = self._events()
         latents_start = self.get_noise(self.seed1)
-        list_latents1 = self.run_diffusion(list_conditionings, latents_start=latents_start, idx_start=0)
+        list_latents1 = self.run_diffusion(list_conditionings, latents_start=latents_start, idx_start=0, noise_key=0.0)
         self._finish_timing(ev0, ev1)
         self.tree_latents[0] = list_latents1
         if return_image:
@@ -368,8 +437,10 @@ class BlendingEngine():
         the two trajectories are independent, or -- with branch-1 crossfeed -- trajectory 2 reads step i-1 of
         trajectory 1, which the lockstep loop has already produced)."""
         self.dh.set_num_inference_steps(self.num_inference_steps)
-        job1 = dict(text_embeddings=self.get_mixed_conditioning(0)[0], latents_start=self.get_noise(self.seed1))
-        job2 = dict(text_embeddings=self.get_mixed_conditioning(1)[0], latents_start=self.get_noise(self.seed2))
+        job1 = dict(text_embeddings=self.get_mixed_conditioning(0)[0], latents_start=self.get_noise(self.seed1),
+                    noise_fn=self._noise_source(0.0))
+        job2 = dict(text_embeddings=self.get_mixed_conditioning(1)[0], latents_start=self.get_noise(self.seed2),
+                    noise_fn=self._noise_source(1.0))
         if self.branch1_crossfeed_power > 0.0:
             job2.update(list_latents_mixing=("job", 0), mixing_coeffs=self._branch1_crossfeed_coeffs())
         ev0, ev1 = self._events()
@@ -385,9 +456,10 @@ class BlendingEngine():
         if self.branch1_crossfeed_power > 0.0:
             mixing_coeffs = self._branch1_crossfeed_coeffs()
             list_latents2 = self.run_diffusion(list_conditionings, latents_start=latents_start, idx_start=0,
-                                               list_latents_mixing=self.tree_latents[0], mixing_coeffs=mixing_coeffs)
+                                               list_latents_mixing=self.tree_latents[0], mixing_coeffs=mixing_coeffs,
+                                               noise_key=1.0)
         else:
-            list_latents2 = self.run_diffusion(list_conditionings, latents_start)
+            list_latents2 = self.run_diffusion(list_conditionings, latents_start, noise_key=1.0)
         self.tree_latents[-1] = list_latents2
         if return_image:
             return self.dh.latent2image(list_latents2[-1])
@@ -441,7 +513,8 @@ class BlendingEngine():
         mixing_coeffs.extend((N - len(mixing_coeffs)) * [0])
         latents_start = list_latents_parental_mix[idx_injection - 1]
         return self.run_diffusion(list_conditionings, latents_start=latents_start, idx_start=idx_injection,
-                                  list_latents_mixing=list_latents_parental_mix, mixing_coeffs=mixing_coeffs)
+                                  list_latents_mixing=list_latents_parental_mix, mixing_coeffs=mixing_coeffs,
+                                  noise_key=fract_mixing)
 
     def get_time_based_branching(self, depth_strength, t_compute_max_allowed=None, nmb_max_branches=None):
         self._resolve_timing()
@@ -514,9 +587,16 @@ class BlendingEngine():
 
     @torch.no_grad()
     def run_diffusion(self, list_conditionings, latents_start=None, idx_start=0, list_latents_mixing=None,
-                      mixing_coeffs=0.0, return_image=False):
+                      mixing_coeffs=0.0, return_image=False, noise_key=None):
         self.dh.set_num_inference_steps(self.num_inference_steps)
         assert type(list_conditionings) is list, "list_conditionings need to be a list"
+        src = self._noise_source(noise_key) if (noise_key is not None and hasattr(self.dh, "pipe")
+                                                and self.dh.pipe is not None) else None
+        if src is not None:
+            out = self.dh.run_diffusion_sd_xl_multi([dict(text_embeddings=list_conditionings[0], latents_start=latents_start,
+                                                          list_latents_mixing=list_latents_mixing,
+                                                          mixing_coeffs=mixing_coeffs, noise_fn=src)], idx_start)[0]
+            return self.dh.latent2image(out[-1]) if return_image else out
         return self.dh.run_diffusion_sd_xl(text_embeddings=list_conditionings[0], latents_start=latents_start,
                                            idx_start=idx_start, list_latents_mixing=list_latents_mixing,
                                            mixing_coeffs=mixing_coeffs, return_image=return_image)

@@ -52,6 +52,9 @@ template <int BN> struct Cfg {
     static constexpr int deep = (BN <= 64) ? 8 : (BN <= 128) ? 7 : (BN <= 160) ? 6 : 4;
     static constexpr int tmem_cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int tmem_cols_single = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : (BN <= 256) ? 256 : 512;
+    // co-resident variant: ring depth such that two CTAs (+ 1 KB reserved each) fit in the SM's 228 KB
+    static constexpr int cr_stages = (BN <= 64) ? 4 : 3;
     static constexpr int smem_bytes(int nst) { return nst * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/; }
     static constexpr int pair_stage_bytes = kABytes + b_bytes / 2;   // bytes ONE CTA of a pair stages per k-block
 };
@@ -95,9 +98,16 @@ __device__ __forceinline__ void ln_row_stats(const GemmParams& p, long long row,
 // Each CTA stages its own A tile and HALF of the weight tile; the leader issues tcgen05.mma.cta_group::2 (M = 256),
 // each SM's tensor core accumulates its 128 rows in its own TMEM and the weight halves are shared across the pair,
 // so per-SM shared-memory traffic (the limiter of single-CTA M=128 MMAs on Blackwell) drops by BN/2 rows per k-block.
-template <int BN, int CL>
-__global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+// CR = 1: the CO-RESIDENT variant for single-wave problems (every CTA owns one tile: the transformer's 2048-row
+// linears).  Shallow smem ring (<= 110 KB) + ONE accumulator (<= 256 TMEM columns) + <= 96 registers, so two CTAs fit
+// on an SM: under PDL the NEXT kernel's CTAs become resident while this kernel is still running, and their prologue
+// (barrier init, TMEM allocation, descriptor prefetch, the first weight tiles) no longer waits for this kernel's CTAs
+// to exit -- with one 200 KB CTA per SM that hand-over (~2 us of a ~10 us kernel) was fully exposed.
+template <int BN, int CL, int CR>
+__global__ void __launch_bounds__(kThreadsGemm, CR ? 2 : 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     using C = Cfg<BN>;
+    constexpr int kAcc = CR ? 1 : 2;            // accumulator buffers in TMEM
+    constexpr int kTmemCols = CR ? C::tmem_cols_single : C::tmem_cols;
     pdl_launch_dependents();       // the next kernel may start its launch + prologue while this one runs
     const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
     extern __shared__ uint8_t smem_raw[];
@@ -130,8 +140,8 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
         fence_mbar_init();
     }
     if (warp == 2) {
-        if (CL == 2) tmem_alloc_2sm(tmem_slot, C::tmem_cols);
-        else tmem_alloc(tmem_slot, C::tmem_cols);
+        if (CL == 2) tmem_alloc_2sm(tmem_slot, kTmemCols);
+        else tmem_alloc(tmem_slot, kTmemCols);
     }
     tc_fence_before();
     __syncthreads();
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
                 else umma_commit(&tmem_full[acc]);
             }
             __syncwarp();
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 2) {
         // ===================== epilogue (8 warps: two per TMEM lane quadrant, splitting the columns) =====================
@@ -411,7 +421,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
                 if (CL == 2) mbar_arrive_cluster(map_to_cta(&tmem_empty[acc], 0));
                 else mbar_arrive(&tmem_empty[acc]);
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -419,8 +429,8 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_tc_kernel(const __grid_c
     __syncthreads();
     if (CL == 2) cluster_sync_all();          // the peer may still arrive on this CTA's barriers / read its smem
     if (warp == 2) {
-        if (CL == 2) tmem_dealloc_2sm(tmem_base, C::tmem_cols);
-        else tmem_dealloc(tmem_base, C::tmem_cols);
+        if (CL == 2) tmem_dealloc_2sm(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -480,11 +490,14 @@ int encode_weight_map(lb_ctx* ctx, CUtensorMap* m, const void* base, int64_t ld,
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-template <int BN, int CL> int launch_bn_cl(const GemmPlan& plan, cudaStream_t st) {
+template <int BN, int CL, int CR> int launch_bn_cl(const GemmPlan& plan, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg<BN>::smem_bytes(Cfg<BN>::deep)));
+        LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL, CR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<BN>::smem_bytes(CR ? Cfg<BN>::cr_stages : Cfg<BN>::deep)));
+        if (CR)     // ask for the full shared-memory carve-out so that two ~110 KB CTAs fit
+            LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL, CR>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg{};
@@ -501,11 +514,15 @@ template <int BN, int CL> int launch_bn_cl(const GemmPlan& plan, cudaStream_t st
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = lb_pdl_enabled() ? 2 : 1;
-    LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, plan.p));
+    LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL, CR>, plan.p));
     return 0;
 }
 template <int BN> int launch_bn(const GemmPlan& plan, cudaStream_t st) {
-    return plan.cluster == 2 ? launch_bn_cl<BN, 2>(plan, st) : launch_bn_cl<BN, 1>(plan, st);
+    if (plan.cluster == 2) return launch_bn_cl<BN, 2, 0>(plan, st);
+    if constexpr (BN <= 160) {
+        if (plan.coresident) return launch_bn_cl<BN, 1, 1>(plan, st);
+    }
+    return launch_bn_cl<BN, 1, 0>(plan, st);
 }
 
 }  // namespace
@@ -630,6 +647,13 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
         const int tiles = p.tiles_m * p.tiles_n;
         plan->grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
     }
+    // co-resident variant: single-wave problems (one tile per CTA) on the single-CTA path
+    {
+        const char* cr_env = getenv("LB_GEMM_CORESIDENT");
+        const bool single_wave = (int64_t)p.tiles_m * p.tiles_n <= ctx->sm_count;
+        plan->coresident = (plan->cluster == 1 && plan->bn <= 160 && single_wave) ? 1 : 0;
+        if (cr_env) plan->coresident = (atoi(cr_env) != 0 && plan->cluster == 1 && plan->bn <= 160) ? 1 : 0;
+    }
     // ring depth: deep for long-K problems (>= 40 k-blocks: the 3x3 convolutions, FF-out), shallow otherwise
     {
         const bool deep = total >= 40 && !getenv("LB_GEMM_SHALLOW");
@@ -637,6 +661,7 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
         const int shallow_st = (bnv <= 64) ? 8 : (bnv <= 128) ? 6 : (bnv <= 160) ? 5 : 4;
         const int deep_st = (bnv <= 64) ? 8 : (bnv <= 128) ? 7 : (bnv <= 160) ? 6 : 4;
         p.stages = deep ? deep_st : shallow_st;
+        if (plan->coresident) p.stages = (bnv <= 64) ? 4 : 3;
     }
     plan->smem_bytes = 0;
     return 0;

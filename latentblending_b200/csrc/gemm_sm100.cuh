@@ -57,6 +57,7 @@ struct GemmPlan {
     int grid;
     int smem_bytes;
     int cluster;   // 1, or 2 = CTA pairs along M sharing the weight tile via TMA multicast
+    int coresident;  // 1 = shallow-ring / single-accumulator variant, two CTAs per SM (single-wave problems)
 };
 
 int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan);

@@ -145,7 +145,7 @@ class DiffusersHolder:
         is exactly run_diffusion_sd_xl's: every kernel on the path is batch-invariant (tests/test_engine_gpu.py).
 
         jobs: dicts with text_embeddings (4-tuple), latents_start, list_latents_mixing, mixing_coeffs and optionally
-        guidance_scale (default: self.guidance_scale).  ``list_latents_mixing`` may be ``("job", j)``: mix against
+        guidance_scale (default: self.guidance_scale) and noise_fn(step, shape) (ancestral noise source of this job).  ``list_latents_mixing`` may be ``("job", j)``: mix against
         the trajectory job j is producing in this very call (branch-1 crossfeed reads step i-1, which job j has
         already written).  Returns one len-N list per job (None for i < idx_start, else [1,4,h,w] fp16 views of that
         job's trajectory slab)."""
@@ -198,7 +198,8 @@ class DiffusersHolder:
         # path) runs trajectory 1 to the end before trajectory 2, so under torch.manual_seed the draws are ordered
         # job-major; the lockstep loop consumes them step-major.  Pre-draw them in the reference's order.
         drawn = None
-        if sched.ancestral and k > 1 and self.noise_fn_multi is None and self.noise_fn is None:
+        if (sched.ancestral and k > 1 and self.noise_fn_multi is None and self.noise_fn is None
+                and all(job.get("noise_fn") is None for job in jobs)):
             drawn = [[torch.randn((1, C, h, w), device=self.device, dtype=torch.float16) for _ in range(idx_start, N)]
                      for _ in jobs]
         scaled = [False] * k          # the previous step's lb_cfg_euler_step already wrote this job's model input
@@ -223,7 +224,10 @@ class DiffusersHolder:
             for j in range(k):
                 noise = None
                 if sched.ancestral:
-                    if k > 1 and self.noise_fn_multi is not None:
+                    if jobs[j].get("noise_fn") is not None:        # per-job source (BlendingEngine.deterministic_noise)
+                        noise = jobs[j]["noise_fn"](i, latents[j].shape).to(device=self.device,
+                                                                            dtype=torch.float16).contiguous()
+                    elif k > 1 and self.noise_fn_multi is not None:
                         noise = self.noise_fn_multi(j, i, latents[j].shape).to(device=self.device,
                                                                                dtype=torch.float16).contiguous()
                     elif self.noise_fn is not None:

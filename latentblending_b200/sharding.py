@@ -199,3 +199,55 @@ class LevelSharder:
         f0 = tree.frames[0]
         n = lat.numel()
         return ((num_steps - idx_injection, n), tuple(f0.shape), lat.dtype, f0.dtype, lat.device)
+
+
+def run_level_local(tree, idx_injection, n_stems, compute_many, similarity, width, on_insert=None, stats=None,
+                    split_ratio=0.6):
+    """Single-GPU speculation: the stems of one level with up to ``width`` candidate branches advanced in LOCKSTEP
+    through one batched UNet forward per step (DiffusersHolder.run_diffusion_sd_xl_multi).  Same planning and replay as
+    LevelSharder.run_level with the ranks replaced by batch slots: candidates = best-first subdivision of the current
+    gaps, replay = the reference's greedy loop consuming cached candidates; mis-speculated candidates stay cached
+    until the level ends.  Every kernel is batch-invariant, so the tree equals the sequential one.  Pays when a
+    batch-k forward costs much less than k batch-1 forwards: SDXL-Turbo at 512^2 (weight-bandwidth / launch bound);
+    not SDXL-base at 1024^2 on one GPU (batch 4 costs 1.76x batch 2).
+
+    compute_many([(mid, p1, p2), ...], idx_injection) -> [(list_latents, frame), ...]"""
+    cache = {}
+    remaining = int(n_stems)
+    ratio = split_ratio
+    while remaining > 0:
+        cands = plan_candidates(tree.tree_fracts, tree.tree_similarities, min(width, remaining), cache, ratio)
+        todo = []
+        for mid, lo, hi in cands:
+            p1, p2 = older_parents(tree.tree_fracts, tree.tree_idx_injection, mid, idx_injection)
+            todo.append((mid, p1, p2))
+        for (mid, _, _), res in zip(todo, compute_many(todo, idx_injection)):
+            cache[mid] = res
+        if stats is not None:
+            stats["rounds"] += 1
+            stats["computed"] += len(todo)
+        while remaining > 0:
+            sims = tree.tree_similarities
+            c1 = 0 if len(sims) == 1 else int(np.argmax(sims))
+            mid = (tree.tree_fracts[c1] + tree.tree_fracts[c1 + 1]) / 2
+            if mid not in cache:
+                break
+            traj, frm = cache.pop(mid)
+            left = similarity(frm, tree.frames[c1])
+            right = similarity(frm, tree.frames[c1 + 1])
+            parent_sim = sims[c1]
+            if isinstance(parent_sim, (int, float, np.floating)) and parent_sim > 0:
+                ratio = 0.7 * ratio + 0.3 * min(1.0, max(left, right) / float(parent_sim))
+            if on_insert is not None:
+                on_insert(mid)
+            k = c1 + 1
+            tree.tree_latents.insert(k, traj)
+            tree.frames.insert(k, frm)
+            tree.tree_fracts.insert(k, mid)
+            tree.tree_idx_injection.insert(k, idx_injection)
+            tree.tree_similarities[c1] = left
+            tree.tree_similarities.insert(k, right)
+            remaining -= 1
+            if stats is not None:
+                stats["used"] += 1
+    return ratio

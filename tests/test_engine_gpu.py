@@ -295,3 +295,33 @@ def test_unforced_transition_places_branches_like_the_oracle_while_margins_allow
     print(f"unforced transition: {compared}/{len(order_o)} decisions above the 10 % margin, all equal; margins "
           f"{[round(m, 3) for m in margins]}")
     assert compared >= 1
+
+
+@pytest.mark.parametrize("turbo", [False, True])
+def test_lockstep_speculation_builds_the_sequential_tree(turbo):
+    """Single-GPU speculation (sharding.run_level_local): up to k candidate branches of a level share one batched UNet
+    forward per step.  Kernels are batch-invariant and mis-speculated candidates are dropped, so tree, latents and
+    similarities equal the strictly sequential engine's bit for bit (Turbo: with per-branch deterministic noise)."""
+    from latentblending_b200 import BlendingEngine
+    _, pp, _ = _pair(turbo, seed=9)
+    res = []
+    for width in (1, 3):
+        be = BlendingEngine(pp, run_benchmark=False)
+        be.set_dimensions((128, 128))
+        be.set_num_inference_steps(4 if turbo else 8)
+        be.set_prompt1("photo of a lake")
+        be.set_prompt2("alien planet")
+        be.set_branching(nmb_max_branches=7) if turbo else be.set_branching(depth_strength=0.5, nmb_max_branches=9)
+        be.speculative_batch = width
+        be.deterministic_noise = True
+        be.output_device_frames = True
+        be.run_transition(fixed_seeds=[7, 8])
+        res.append((list(be.tree_fracts), [int(v) for v in be.tree_idx_injection], [float(s) for s in be.tree_similarities],
+                    torch.stack([t[-1] for t in be.tree_latents]).clone(), dict(be.spec_stats), float(be.guidance_scale)))
+    a, b = res
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+    assert torch.equal(a[3], b[3])
+    assert a[5] == b[5]                                  # same guidance state left behind
+    assert b[4]["used"] == len(a[0]) - 2 - (0 if turbo else sum(1 for s in be.list_nmb_stems if int(s) == 1))
+    assert b[4]["rounds"] < b[4]["used"]                 # speculation saved rounds
+    print("speculation stats", b[4])
