@@ -59,7 +59,21 @@ template <int BN> struct Cfg {
     static constexpr int pair_stage_bytes = kABytes + b_bytes / 2;   // bytes ONE CTA of a pair stages per k-block
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below
+// the fp16 rounding the reference applies to gelu(gate)): ~14 FMA-pipe instructions + MUFU.RCP + MUFU.EX2 instead
+// of erff's two-branch polynomial -- the GEGLU epilogue of the FF-in GEMMs was issue-bound next to a K = 1280 main loop.
+// For z < 0, 1 + erf(z) = erfc(|z|) is formed directly (no cancellation in the negative tail).
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erfc_abs = poly * t * exp2f(-1.4426950408889634f * z * z);     // erfc(|z|)
+    const float one_plus_erf = x >= 0.f ? 2.0f - erfc_abs : erfc_abs;
+    return 0.5f * x * one_plus_erf;
+}
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     const __half2* h = reinterpret_cast<const __half2*>(&v);
@@ -76,17 +90,28 @@ __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-// (mu, rstd) of one row of the LayerNorm-folded A operand from the producer's per-row partial sums (fixed order)
+// (mu, rstd) of one row of the LayerNorm-folded A operand from the producer's per-row partial sums (fixed order).
+// The partials of a row are contiguous (<= 64 x float2): they are fetched as float4 pairs, eight loads in flight at
+// a time -- a scalar loop over them serialises ~16 L2 round trips (10k clk per tile: slower than the LayerNorm
+// launches the fold removes; measured in r02a).
 __device__ __forceinline__ void ln_row_stats(const GemmParams& p, long long row, bool ok, float& mu, float& rstd) {
     mu = 0.f;
     rstd = 1.f;
     if (!ok) return;
     float s = 0.f, q = 0.f;
-    const float2* st = p.ln_stats + row * p.ln_parts;
-    for (int i = 0; i < p.ln_parts; ++i) {
-        const float2 v = __ldcg(st + i);
-        s += v.x;
-        q += v.y;
+    const float4* st = reinterpret_cast<const float4*>(p.ln_stats + row * p.ln_parts);   // ln_parts is even
+    const int pairs = p.ln_parts >> 1;
+    for (int base = 0; base < pairs; base += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (base + i < pairs) ? __ldcg(st + base + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s += v[i].x;
+            q += v[i].y;
+            s += v[i].z;
+            q += v[i].w;
+        }
     }
     mu = s * p.ln_inv_k;
     double var = (double)q * (double)p.ln_inv_k - (double)mu * (double)mu;
@@ -564,8 +589,8 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
     // --- N tiling
     int bn;
     if ((d.mode & 0xff) == 1) {
-        bn = 128;
-        LB_REQUIRE(d.N % 128 == 0, "gemm: GEGLU needs N %% 128 == 0 (got %d)", d.N);
+        bn = (d.mode & LB_GEMM_GEGLU256) ? 256 : 128;      // the weight rows are interleaved per N tile by the caller
+        LB_REQUIRE(d.N % bn == 0, "gemm: GEGLU needs N %% %d == 0 (got %d)", bn, d.N);
     } else if (d.N % 256 == 0 && (int64_t)p.tiles_m * (d.N / 256) >= 2 * ctx->sm_count) bn = 256;
     else if (d.N % 160 == 0) bn = 160;
     else if (d.N % 128 == 0) bn = 128;

@@ -278,8 +278,9 @@ def _fold_layernorm(w, bias, gamma, beta):
     return wf, csum, lnb.contiguous()
 
 
-def _geglu_perm(inner, device):
-    idx = torch.arange(inner, device=device).view(-1, 64)
+def _geglu_perm(inner, device, half=64):
+    """Row order of the GEGLU projection for the kernel's N tiles: ``half`` value rows then their ``half`` gate rows."""
+    idx = torch.arange(inner, device=device).view(-1, half)
     return torch.stack([idx, idx + inner], dim=1).reshape(-1)
 
 

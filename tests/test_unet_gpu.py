@@ -1,7 +1,7 @@
 """GPU parity of the lowered UNet program (liblb200) against the CPU oracle UNet
 (oracle/sdxl_unet.py, fp32) on identical seeded weights and inputs.
-Tolerance (stated): relative L2 error of eps <= 5e-3 -- fp16 storage of every
-activation with fp32 accumulation vs an all-fp32 oracle.  At the BENCHMARKED shape
+Tolerance (stated): relative L2 error of eps <= 2e-3 -- fp16 storage of every
+activation with fp32 accumulation vs an all-fp32 oracle; measured 5.0e-4 ... 5.2e-4 (r02a).  At the BENCHMARKED shape
 (full SDXL-base, CFG batch 2, 128x128 latents) the comparison is against the committed
 fixture tests/golden/unet_sdxl_b2_128.npz (tests/golden/make_fullsize_fixtures.py).
 Measured rel-L2 values are printed (-s) and recorded in DESIGN.md section 5."""
@@ -49,7 +49,7 @@ def test_tiny_unet_matches_oracle(B, h, w, t):
     from oracle.sdxl_unet import tiny_config
     rel, eps, ref, net = _run_pair(tiny_config(), B, h, w, t)
     assert torch.isfinite(eps).all()
-    assert rel <= 5e-3, f"relative L2 error {rel}"
+    assert rel <= 2e-3, f"relative L2 error {rel}"
     # replaying the recorded program is deterministic
     x, ctx, pooled, tids = _inputs(tiny_config(), B, h, w)
     again = net.forward(x.cuda(), t, ctx.cuda(), pooled.cuda(), tids.cuda()).float().cpu()
@@ -63,7 +63,7 @@ def test_medium_unet_matches_oracle():
                       addition_time_embed_dim=64, pooled_dim=128, sample_size=32)
     rel, eps, ref, _ = _run_pair(ocfg, 2, 32, 32, 499.0)
     assert torch.isfinite(eps).all()
-    assert rel <= 5e-3, f"relative L2 error {rel}"
+    assert rel <= 2e-3, f"relative L2 error {rel}"
 
 
 _FULL = {}
@@ -96,7 +96,7 @@ def test_full_sdxl_unet_matches_oracle_at_256px():
     rel = ((eps - ref).norm() / ref.norm()).item()
     print(f"full SDXL UNet @32x32 B=2: rel_l2={rel:.3e}")
     assert torch.isfinite(eps).all()
-    assert rel <= 5e-3, f"relative L2 error {rel}"
+    assert rel <= 2e-3, f"relative L2 error {rel}"
     assert full["net"].launches_per_forward(2, 32, 32)[0] > 600
 
 
@@ -122,7 +122,7 @@ def test_full_sdxl_unet_matches_fixture_at_bench_shape():
     mse = ((eps - ref) ** 2).mean().item()
     print(f"full SDXL UNet @128x128 B=2 (bench shape): rel_l2={rel:.3e} mse={mse:.3e} max={float((eps - ref).abs().max()):.3e}")
     assert torch.isfinite(eps).all()
-    assert rel <= 5e-3, f"relative L2 error {rel}"
+    assert rel <= 2e-3, f"relative L2 error {rel}"
     # batch invariance at the bench shape: each CFG half alone reproduces its half of the batch-2 forward bit for bit
     # (what the multi-GPU CFG split and the lockstep batching rely on)
     for b in range(2):

@@ -37,7 +37,7 @@ traffic)
   timeout 900 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
      --clock-control none --csv --log-file $O/unet_traffic.csv python tools/profile_unet.py > $O/unet_traffic.log 2>&1; echo "traffic exit $?"
   timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
-     -k regex:slerp_l2 -s 5 -c 2 --log-file $O/mix_traffic.csv python tools/bench_mix.py > $O/mix_traffic.log 2>&1; echo "mix traffic exit $?" ;;
+     -k regex:slerp_l2 -s 105 -c 2 --log-file $O/mix_traffic.csv python tools/bench_mix.py > $O/mix_traffic.log 2>&1; echo "mix traffic exit $?" ;;
 small)
   timeout 300 python tools/bench_small.py > $O/bench_small.txt 2>&1; cat $O/bench_small.txt ;;
 ncu_small)
@@ -45,6 +45,9 @@ ncu_small)
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_small.py > $O/ncu_small.log 2>&1; echo "ncu small exit $?" ;;
 cluster2)
   LB_GEMM_CLUSTER=2 timeout 300 python tools/bench_ops.py gemm > $O/bench_ops_cluster2.txt 2>&1; cat $O/bench_ops_cluster2.txt ;;
+dual)
+  timeout 300 python tools/time_dual_stream.py > $O/dual_stream.txt 2>&1; cat $O/dual_stream.txt
+  LB_GEMM_CORESIDENT=0 timeout 300 python tools/time_dual_stream.py > $O/dual_stream_nocr.txt 2>&1; cat $O/dual_stream_nocr.txt ;;
 lnfold)
   timeout 300 python tools/time_unet_batch.py > $O/unet_batch_lnfold.txt 2>&1; cat $O/unet_batch_lnfold.txt
   LB_NO_LN_FOLD=1 timeout 300 python tools/time_unet_batch.py > $O/unet_batch_nofold.txt 2>&1; cat $O/unet_batch_nofold.txt ;;
