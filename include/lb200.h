@@ -284,6 +284,9 @@ typedef struct lb_op {
 typedef struct lb_program lb_program;
 int     lb_program_create(lb_ctx* ctx, const lb_op* ops, int64_t n_ops, lb_program** out);
 int     lb_program_run(lb_program* prog, float t, void* stream);
+/* replay mode of lb_program_run: 1 = one CUDA-graph launch per run (captured on the second run, every launch keeps its
+ * programmatic-dependent-launch edge), 0 = not captured yet, -1 = direct launches (capture unavailable or LB_NO_GRAPH) */
+int     lb_program_is_graph(lb_program* prog);
 /* profiling aid: replay only the ops whose kind bit (1u << LB_OP_*) is set in kind_mask */
 int     lb_program_run_kinds(lb_program* prog, float t, uint32_t kind_mask, void* stream);
 int64_t lb_program_count_kinds(lb_program* prog, uint32_t kind_mask);

@@ -121,6 +121,7 @@ SIGNATURES = {
     "lb_program_create": (c_int, [c_void_p, ctypes.POINTER(Op), c_int64, ctypes.POINTER(c_void_p)]),
     "lb_program_run": (c_int, [c_void_p, c_float, c_void_p]),
     "lb_program_num_launches": (c_int64, [c_void_p]),
+    "lb_program_is_graph": (c_int, [c_void_p]),
     "lb_program_run_kinds": (c_int, [c_void_p, c_float, ctypes.c_uint32, c_void_p]),
     "lb_program_count_kinds": (c_int64, [c_void_p, ctypes.c_uint32]),
     "lb_program_destroy": (c_int, [c_void_p]),

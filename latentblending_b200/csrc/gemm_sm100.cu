@@ -676,8 +676,12 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
     {
         const char* cr_env = getenv("LB_GEMM_CORESIDENT");
         const bool single_wave = (int64_t)p.tiles_m * p.tiles_n <= ctx->sm_count;
-        plan->coresident = (plan->cluster == 1 && plan->bn <= 160 && single_wave) ? 1 : 0;
-        if (cr_env) plan->coresident = (atoi(cr_env) != 0 && plan->cluster == 1 && plan->bn <= 160) ? 1 : 0;
+        // Measured (r02b): with only 3 ring stages the TMA round trip (~1900 clk vs 256-320 clk per k-block) is no longer
+        // hidden -- conv 2048x1280x11520 45 -> 75 us, to_out 2048x1280x1280 11.6 -> 16.2 us, UNet step 23.5 -> 26.1 ms.
+        // The variant therefore stays OFF unless LB_GEMM_CORESIDENT=1 asks for it (kept for the record of the experiment).
+        (void)single_wave;
+        plan->coresident = 0;
+        if (cr_env) plan->coresident = (atoi(cr_env) != 0 && plan->cluster == 1 && plan->bn <= 160 && single_wave) ? 1 : 0;
     }
     // ring depth: deep for long-K problems (>= 40 k-blocks: the 3x3 convolutions, FF-out), shallow otherwise
     {

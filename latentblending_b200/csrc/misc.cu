@@ -18,11 +18,15 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x));
 // temb_in[b, :dim_t]            = [cos(t*f_i) | sin(t*f_i)],  f_i = exp(-ln(1e4) * i / (dim_t/2))
 // add_in[b, :pooled]            = text_embeds[b]
 // add_in[b, pooled + 6*j ...]   = sinusoid(time_ids[b, j], dim_a)   (flip_sin_to_cos: cos first)
-__global__ void embed_inputs_kernel(float t, const __half* __restrict__ text_embeds, const __half* __restrict__ time_ids,
+// t_dev (optional): the timestep is read from device memory instead of the launch parameter, so that a CUDA graph of
+// the whole UNet program can be replayed for any timestep (program.cu).
+__global__ void embed_inputs_kernel(float t, const float* __restrict__ t_dev, const __half* __restrict__ text_embeds,
+                                    const __half* __restrict__ time_ids,
                                     int B, int dim_t, int pooled, int dim_a, __half* __restrict__ temb_in,
                                     __half* __restrict__ add_in) {
     pdl_launch_dependents();
     pdl_wait();
+    if (t_dev != nullptr) t = *t_dev;
     const int b = blockIdx.x;
     const int half_t = dim_t / 2, half_a = dim_a / 2;
     const int add_w = pooled + 6 * dim_a;
@@ -259,12 +263,29 @@ unsigned grid_for(long long work_items, int sm) {
 
 }  // namespace
 
-extern "C" int lb_embed_inputs(lb_ctx* ctx, float t, const void* text_embeds, const void* time_ids, int B,
-                               int dim_t, int pooled, int dim_a, void* temb_in, void* add_in, void* stream) {
+// internal: t from device memory when t_dev != NULL (graph replay), else the launch parameter
+int lb_embed_inputs_src(lb_ctx* ctx, float t, const float* t_dev, const void* text_embeds, const void* time_ids, int B,
+                        int dim_t, int pooled, int dim_a, void* temb_in, void* add_in, void* stream) {
     LB_REQUIRE(ctx && text_embeds && time_ids && temb_in && add_in, "lb_embed_inputs: null argument");
     LB_REQUIRE(dim_t % 2 == 0 && dim_a % 2 == 0 && B >= 1, "lb_embed_inputs: bad sizes");
-    lb_launch_pdl(embed_inputs_kernel, B, kThreads, 0, lb_stream(stream), t, (const __half*)text_embeds, (const __half*)time_ids, B,
-                                                              dim_t, pooled, dim_a, (__half*)temb_in, (__half*)add_in);
+    lb_launch_pdl(embed_inputs_kernel, B, kThreads, 0, lb_stream(stream), t, t_dev, (const __half*)text_embeds,
+                  (const __half*)time_ids, B, dim_t, pooled, dim_a, (__half*)temb_in, (__half*)add_in);
+    LB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lb_embed_inputs(lb_ctx* ctx, float t, const void* text_embeds, const void* time_ids, int B,
+                               int dim_t, int pooled, int dim_a, void* temb_in, void* add_in, void* stream) {
+    return lb_embed_inputs_src(ctx, t, nullptr, text_embeds, time_ids, B, dim_t, pooled, dim_a, temb_in, add_in, stream);
+}
+
+__global__ void set_scalar_kernel(float* dst, float v) {
+    pdl_launch_dependents();
+    pdl_wait();
+    *dst = v;
+}
+int lb_set_scalar(float* dst_dev, float v, cudaStream_t st) {
+    lb_launch_pdl(set_scalar_kernel, 1, 1, 0, st, dst_dev, v);
     LB_LAUNCH_CHECK();
     return 0;
 }

@@ -94,16 +94,42 @@ gn_partial_kernel(const __half* __restrict__ x, long long ld, int C, int HW, int
     __syncthreads();
     if (s_last) {
         __threadfence();
+        // All 256 threads of the last block combine the chunk partials: thread (slice, g) sums chunks slice, slice + S,
+        // ... of group g in fp64 with 8 loads in flight, then the S slices are added in slice order -- a fixed
+        // summation order (deterministic, batch-invariant).  One thread per group walking all ~300 chunks was a serial
+        // chain of L2 round trips: ~20 us, most of this kernel's time on the large activations (r02a).
+        __shared__ double f_sum[kThreads], f_sq[kThreads];
+        const int S = kThreads / groups;                 // slices (groups <= 64 -> S >= 4)
+        const int g = threadIdx.x % groups, slice = threadIdx.x / groups;
+        double s = 0.0, q = 0.0;
+        if (slice < S) {
+            const float2* pp = partial + (long long)b * chunks * groups + g;
+            for (int c0 = slice; c0 < chunks; c0 += 8 * S) {
+                float2 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = c0 + i * S;
+                    v[i] = c < chunks ? __ldcg(pp + (long long)c * groups) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    s += v[i].x;
+                    q += v[i].y;
+                }
+            }
+        }
+        f_sum[threadIdx.x] = s;
+        f_sq[threadIdx.x] = q;
+        __syncthreads();
         if (threadIdx.x < groups) {
-            double s = 0.0, q = 0.0;
-            for (int c = 0; c < chunks; ++c) {
-                const float2 v = __ldcg(&partial[((long long)b * chunks + c) * groups + threadIdx.x]);
-                s += v.x;
-                q += v.y;
+            double ts = 0.0, tq = 0.0;
+            for (int sl = 0; sl < S; ++sl) {
+                ts += f_sum[sl * groups + threadIdx.x];
+                tq += f_sq[sl * groups + threadIdx.x];
             }
             const double n = (double)HW * cpg;
-            const double mean = s / n;
-            double var = q / n - mean * mean;
+            const double mean = ts / n;
+            double var = tq / n - mean * mean;
             if (var < 0.0) var = 0.0;
             stats[(long long)b * groups + threadIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
         }

@@ -5,6 +5,8 @@
 // turns them into prepared launches once (TMA descriptors encoded, tilings chosen) and
 // replays them on a stream with no Python, no allocation and no host sync in the loop.
 // Replaces the eager PyTorch module walk behind pipe.unet(...) (diffusers_holder.py:336-344).
+#include <stdlib.h>
+
 #include <vector>
 
 #include "gemm_sm100.cuh"
@@ -14,6 +16,15 @@ int attn_plan_build_opaque(lb_ctx* ctx, const lb_attn_desc& d, void** plan_out);
 int attn_plan_launch_opaque(void* plan, cudaStream_t st);
 void attn_plan_free_opaque(void* plan);
 
+int lb_embed_inputs_src(lb_ctx* ctx, float t, const float* t_dev, const void* text_embeds, const void* time_ids, int B,
+                        int dim_t, int pooled, int dim_a, void* temb_in, void* add_in, void* stream);
+int lb_set_scalar(float* dst_dev, float v, cudaStream_t st);
+
+// Replay mode.  The op list is static, so after one warm (direct) run the whole program is captured ONCE into a CUDA
+// graph -- every launch keeps its programmatic-dependent-launch edge -- and later runs are a single cudaGraphLaunch:
+// ~700-900 driver launches per UNet forward (2-4 ms of host time) become one, and the device's front end walks a
+// pre-built launch list.  The only run-time parameter, the timestep, lives in device memory (t_dev).  If capture is not
+// possible (another capture in flight, an unsupported driver) the program keeps launching directly.
 struct lb_program {
     lb_ctx* ctx;
     struct Node {
@@ -22,7 +33,17 @@ struct lb_program {
         void* attn;
     };
     std::vector<Node> nodes;
+    float* t_dev = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    int runs = 0;
+    int graph_state = 0;      // 0 not tried, 1 captured, -1 unavailable
 };
+
+static bool lb_graphs_enabled() {
+    static int v = -1;
+    if (v < 0) v = getenv("LB_NO_GRAPH") ? 0 : 1;
+    return v != 0;
+}
 
 extern "C" int lb_program_create(lb_ctx* ctx, const lb_op* ops, int64_t n_ops, lb_program** out) {
     LB_REQUIRE(ctx && ops && out && n_ops >= 0, "lb_program_create: bad arguments");
@@ -59,6 +80,11 @@ extern "C" int lb_program_create(lb_ctx* ctx, const lb_op* ops, int64_t n_ops, l
             return e;
         }
     }
+    if (cudaMalloc(&prog->t_dev, sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        prog->t_dev = nullptr;
+        prog->graph_state = -1;
+    }
     *out = prog;
     return 0;
 }
@@ -66,6 +92,8 @@ extern "C" int lb_program_create(lb_ctx* ctx, const lb_op* ops, int64_t n_ops, l
 extern "C" int lb_program_destroy(lb_program* prog) {
     if (prog) {
         for (auto& nd : prog->nodes) if (nd.attn) attn_plan_free_opaque(nd.attn);
+        if (prog->graph_exec) cudaGraphExecDestroy(prog->graph_exec);
+        if (prog->t_dev) cudaFree(prog->t_dev);
         delete prog;
     }
     return 0;
@@ -78,9 +106,39 @@ extern "C" int64_t lb_program_num_launches(lb_program* prog) {
     return n;
 }
 
+static int program_launch_all(lb_program* prog, float t, const float* t_dev, uint32_t kind_mask, void* stream);
+
 extern "C" int lb_program_run(lb_program* prog, float t, void* stream) {
-    return lb_program_run_kinds(prog, t, 0xFFFFFFFFu, stream);
+    LB_REQUIRE(prog != nullptr, "lb_program_run: null program");
+    cudaStream_t st = lb_stream(stream);
+    if (!lb_graphs_enabled() || prog->graph_state < 0 || prog->nodes.size() < 8)
+        return program_launch_all(prog, t, nullptr, 0xFFFFFFFFu, stream);
+    if (prog->graph_state == 0) {
+        if (prog->runs++ == 0)                       // first run direct: function attributes get set outside a capture
+            return program_launch_all(prog, t, nullptr, 0xFFFFFFFFu, stream);
+        cudaGraph_t graph = nullptr;
+        int e = 1;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            e = program_launch_all(prog, t, prog->t_dev, 0xFFFFFFFFu, stream);
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (e == 0 && ce == cudaSuccess && graph != nullptr &&
+                cudaGraphInstantiate(&prog->graph_exec, graph, 0) == cudaSuccess)
+                prog->graph_state = 1;
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (prog->graph_state != 1) {
+            cudaGetLastError();                       // clear the capture error: replay stays on direct launches
+            prog->graph_state = -1;
+            prog->graph_exec = nullptr;
+            return program_launch_all(prog, t, nullptr, 0xFFFFFFFFu, stream);
+        }
+    }
+    if (int e = lb_set_scalar(prog->t_dev, t, st)) return e;
+    LB_CHECK_CUDA(cudaGraphLaunch(prog->graph_exec, st));
+    return 0;
 }
+
+extern "C" int lb_program_is_graph(lb_program* prog) { return prog ? prog->graph_state : -2; }
 
 extern "C" int64_t lb_program_count_kinds(lb_program* prog, uint32_t kind_mask) {
     if (!prog) return -1;
@@ -92,6 +150,10 @@ extern "C" int64_t lb_program_count_kinds(lb_program* prog, uint32_t kind_mask) 
 
 extern "C" int lb_program_run_kinds(lb_program* prog, float t, uint32_t kind_mask, void* stream) {
     LB_REQUIRE(prog != nullptr, "lb_program_run: null program");
+    return program_launch_all(prog, t, nullptr, kind_mask, stream);
+}
+
+static int program_launch_all(lb_program* prog, float t, const float* t_dev, uint32_t kind_mask, void* stream) {
     lb_ctx* ctx = prog->ctx;
     cudaStream_t st = lb_stream(stream);
     for (size_t i = 0; i < prog->nodes.size(); ++i) {
@@ -104,8 +166,8 @@ extern "C" int lb_program_run_kinds(lb_program* prog, float t, uint32_t kind_mas
             case LB_OP_ATTENTION: e = attn_plan_launch_opaque(nd.attn, st); break;
             case LB_OP_EMBED_INPUTS: {
                 const auto& a = o.u.embed;
-                e = lb_embed_inputs(ctx, t, a.text_embeds, a.time_ids, a.B, a.dim_t, a.pooled, a.dim_a, a.temb_in,
-                                    a.add_in, stream);
+                e = lb_embed_inputs_src(ctx, t, t_dev, a.text_embeds, a.time_ids, a.B, a.dim_t, a.pooled, a.dim_a,
+                                        a.temb_in, a.add_in, stream);
                 break;
             }
             case LB_OP_LINEAR_SMALL: {

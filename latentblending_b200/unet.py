@@ -26,7 +26,7 @@ from typing import Tuple
 import torch
 
 from . import _cabi
-from ._cabi import (GEMM_RELU, GEMM_STATIC_W, OP_ATTENTION, OP_CONV_IN, OP_CONV_OUT, OP_EMBED_INPUTS, OP_GEMM,
+from ._cabi import (GEMM_GEGLU256, GEMM_RELU, GEMM_STATIC_W, OP_ATTENTION, OP_CONV_IN, OP_CONV_OUT, OP_EMBED_INPUTS, OP_GEMM,
                     OP_GROUPNORM, OP_IM2COL, OP_IM2COL_S2, OP_LATENT_PREP, OP_LAYERNORM, OP_LINEAR_SMALL,
                     OP_LPIPS_IM2COL_U8, OP_MAXPOOL3S2, OP_POSTPROCESS_U8, OP_SOFTMAX_ROWS, OP_UPSAMPLE2X, Op, check, ctx,
                     stream_ptr)
@@ -287,10 +287,11 @@ def _geglu_perm(inner, device, half=64):
 class PackedUNet:
     """fp16 device copies of the UNet parameters in the layouts the kernels consume."""
 
-    def __init__(self, cfg: UNetConfig, state_dict, device, fold_ln=True):
+    def __init__(self, cfg: UNetConfig, state_dict, device, fold_ln=True, geglu_tile=128):
         self.cfg = cfg
         self.device = torch.device(device)
         self.fold_ln = fold_ln
+        self.geglu_tile = geglu_tile          # N tile of the GEGLU FF-in GEMM: its weight rows are interleaved per tile
         sd = state_dict
         dev = self.device
 
@@ -353,7 +354,7 @@ class PackedUNet:
                 W[t + ".attn2.kv.w"] = torch.cat([g(t + ".attn2.to_k.weight"), g(t + ".attn2.to_v.weight")], 0).contiguous()
                 W[t + ".attn2.out.w"], W[t + ".attn2.out.b"] = g(t + ".attn2.to_out.0.weight"), g(t + ".attn2.to_out.0.bias")
                 pw, pb = g(t + ".ff.net.0.proj.weight"), g(t + ".ff.net.0.proj.bias")
-                perm = _geglu_perm(pw.shape[0] // 2, dev)
+                perm = _geglu_perm(pw.shape[0] // 2, dev, half=geglu_tile // 2)
                 if fold_ln:
                     # LayerNorm folded into the consuming GEMM (include/lb200.h): w' = w*gamma, csum = rowsum(w'),
                     # lnb = w beta + bias
@@ -389,7 +390,13 @@ class UNetB200:
         if fold_ln is None:
             fold_ln = os.environ.get("LB_NO_LN_FOLD") is None
         self.fold_ln = fold_ln
-        self.packed = PackedUNet(cfg, state_dict, self.device, fold_ln=fold_ln)
+        # GEGLU N tile: 256 when every FF inner width allows it (4*C % 128 == 0) and LB_GEGLU_TILE does not say otherwise
+        tile = int(os.environ.get("LB_GEGLU_TILE", "128"))
+        widths = [c for c, d in zip(cfg.block_out_channels, cfg.transformer_layers) if d]
+        if tile == 256 and any((8 * c) % 256 for c in widths):
+            tile = 128
+        self.geglu_tile = tile
+        self.packed = PackedUNet(cfg, state_dict, self.device, fold_ln=fold_ln, geglu_tile=tile)
         self._plans = {}
 
     # -- public -----------------------------------------------------------------------------
@@ -516,6 +523,7 @@ class _Lowering:
         kv_cache = {}
 
         fold = net.fold_ln
+        geglu_mode = 1 | (GEMM_GEGLU256 if net.geglu_tile == 256 else 0)
         f32 = dict(dtype=torch.float32, device=dev)
 
         def transformer(aname, x, C, level, out):
@@ -558,7 +566,7 @@ class _Lowering:
                     P.gemm(hs, Wt[t + ".attn2.q.w"], C, 1, 1, M, q, ln=ln_of(t, ".attn2.q"))
                     P.attention(q, kv, kv, att, B, heads, S, 77, 0, 0, C, cfg.head_dim ** -0.5)
                     P.gemm(att, Wt[t + ".attn2.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".attn2.out.b"], res=hs, stats_out=stats)
-                    P.gemm(hs, Wt[t + ".ff.in.w"], 8 * C, 1, 1, M, gg, mode=1, ln=ln_of(t, ".ff.in"))
+                    P.gemm(hs, Wt[t + ".ff.in.w"], 8 * C, 1, 1, M, gg, mode=geglu_mode, ln=ln_of(t, ".ff.in"))
                     P.gemm(gg, Wt[t + ".ff.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".ff.out.b"], res=hs, stats_out=stats)
                     continue
                 ln = scratch("ln", M, C)
@@ -571,7 +579,7 @@ class _Lowering:
                 P.attention(q, kv, kv, att, B, heads, S, 77, 0, 0, C, cfg.head_dim ** -0.5)
                 P.gemm(att, Wt[t + ".attn2.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".attn2.out.b"], res=hs)
                 P.layernorm(hs, Wt[t + ".norm3.g"], Wt[t + ".norm3.b"], 1e-5, ln)
-                P.gemm(ln, Wt[t + ".ff.in.w"], 8 * C, 1, 1, M, gg, bias=Wt[t + ".ff.in.b"], mode=1)
+                P.gemm(ln, Wt[t + ".ff.in.w"], 8 * C, 1, 1, M, gg, bias=Wt[t + ".ff.in.b"], mode=geglu_mode)
                 P.gemm(gg, Wt[t + ".ff.out.w"], C, 1, 1, M, hs, bias=Wt[t + ".ff.out.b"], res=hs)
             P.gemm(hs, Wt[aname + ".proj_out.w"], C, 1, 1, M, out, bias=Wt[aname + ".proj_out.b"], res=x)
 

@@ -3,6 +3,8 @@ bracketed with cudaProfilerStart/Stop: use `ncu --profile-from-start off ...`.""
 import os
 import sys
 
+os.environ.setdefault("LB_NO_GRAPH", "1")     # profile the direct launches (one ncu record per kernel either way)
+
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -10,7 +10,9 @@ from latentblending_b200.unet import UNetB200  # noqa: E402
 
 dev = "cuda:0"
 net = UNetB200(SDXL_BASE, random_state_dict(unet_param_shapes(SDXL_BASE), 0, dev), dev)
-for B in (2, 4, 6, 8):
+import json
+BATCHES = [int(a) for a in sys.argv[1:]] or [2, 4, 6, 8]
+for B in BATCHES:
     plan = net.plan(B, 128, 128)
     plan.prog_ctx.run()
     for _ in range(3):
@@ -23,7 +25,10 @@ for B in (2, 4, 6, 8):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 8
-    print(f'{{"B": {B}, "unet_step_ms": {ms:.3f}, "ms_per_cfg_pair": {ms / (B // 2):.3f}}}', flush=True)
+    from latentblending_b200 import _cabi
+    print(json.dumps(dict(B=B, unet_step_ms=round(ms, 3), ms_per_cfg_pair=round(ms / max(1, B // 2), 3),
+                          graph=int(_cabi.load().lb_program_is_graph(plan.prog_step.handle)),
+                          env={k: v for k, v in os.environ.items() if k.startswith("LB_")})), flush=True)
     del plan
     net._plans.clear()
     torch.cuda.empty_cache()
