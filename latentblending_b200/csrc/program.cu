@@ -34,6 +34,7 @@ struct lb_program {
     };
     std::vector<Node> nodes;
     float* t_dev = nullptr;
+    cudaStream_t capture_stream = nullptr;   // private: the caller's stream may be the legacy default stream, which cannot capture
     cudaGraphExec_t graph_exec = nullptr;
     int runs = 0;
     int graph_state = 0;      // 0 not tried, 1 captured, -1 unavailable
@@ -93,6 +94,7 @@ extern "C" int lb_program_destroy(lb_program* prog) {
     if (prog) {
         for (auto& nd : prog->nodes) if (nd.attn) attn_plan_free_opaque(nd.attn);
         if (prog->graph_exec) cudaGraphExecDestroy(prog->graph_exec);
+        if (prog->capture_stream) cudaStreamDestroy(prog->capture_stream);
         if (prog->t_dev) cudaFree(prog->t_dev);
         delete prog;
     }
@@ -118,9 +120,14 @@ extern "C" int lb_program_run(lb_program* prog, float t, void* stream) {
             return program_launch_all(prog, t, nullptr, 0xFFFFFFFFu, stream);
         cudaGraph_t graph = nullptr;
         int e = 1;
-        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            e = program_launch_all(prog, t, prog->t_dev, 0xFFFFFFFFu, stream);
-            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (prog->capture_stream == nullptr &&
+            cudaStreamCreateWithFlags(&prog->capture_stream, cudaStreamNonBlocking) != cudaSuccess)
+            prog->capture_stream = nullptr;
+        if (prog->capture_stream != nullptr &&
+            cudaStreamBeginCapture(prog->capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            // nothing executes during capture: the launches only record the node list (with their PDL edges)
+            e = program_launch_all(prog, t, prog->t_dev, 0xFFFFFFFFu, prog->capture_stream);
+            cudaError_t ce = cudaStreamEndCapture(prog->capture_stream, &graph);
             if (e == 0 && ce == cudaSuccess && graph != nullptr &&
                 cudaGraphInstantiate(&prog->graph_exec, graph, 0) == cudaSuccess)
                 prog->graph_state = 1;

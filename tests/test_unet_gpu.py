@@ -56,6 +56,32 @@ def test_tiny_unet_matches_oracle(B, h, w, t):
     assert torch.equal(again, eps)
 
 
+def test_tiny_unet_with_layernorm_fold_matches_oracle():
+    """The optional LayerNorm-folded lowering (UNetB200(fold_ln=True)): same tolerance as the default path."""
+    from latentblending_b200 import ops
+    from latentblending_b200.unet import UNetB200, UNetConfig
+    from oracle.sdxl_unet import SDXLUNet, synthetic_init_, tiny_config
+    ocfg = tiny_config()
+    oracle = synthetic_init_(SDXLUNet(ocfg), seed=0).eval()
+    with torch.no_grad():
+        for p in oracle.parameters():
+            p.copy_(p.half().float())
+    cfg = UNetConfig(**{f.name: getattr(ocfg, f.name) for f in dataclasses.fields(ocfg)})
+    x, ctx, pooled, tids = _inputs(ocfg, 2, 32, 16, 0)
+    with torch.no_grad():
+        ref = oracle(x.float(), 321.0, ctx.float(), pooled.float(), tids.float())
+    rels = {}
+    for fold in (False, True):
+        net = UNetB200(cfg, oracle.state_dict(), "cuda:0", fold_ln=fold)
+        eps = net.forward(x.cuda(), 321.0, ctx.cuda(), pooled.cuda(), tids.cuda()).float().cpu()
+        rels[fold] = ((eps - ref).norm() / ref.norm()).item()
+        n_ln = sum(1 for op in net.plan(2, 32, 16).prog_step.ops if op.kind == 4)
+        assert (n_ln == 0) == fold
+    assert ops.error_flag() == 0
+    print(f"tiny UNet rel_l2: unfused LN {rels[False]:.3e}, LN folded into the GEMMs {rels[True]:.3e}")
+    assert rels[True] <= 2e-3 and rels[False] <= 2e-3
+
+
 def test_medium_unet_matches_oracle():
     """SDXL topology (transformer depths 0/2/10, 10/20 heads ...) at reduced width."""
     from oracle.sdxl_unet import UNetConfig

@@ -51,12 +51,12 @@ dual)
 ab)
   # same-box A/B of the UNet step (batch 2): default | no LN fold | no graph | GEGLU tile 256 | no PDL
   : > $O/ab.txt
-  for e in "" "LB_NO_LN_FOLD=1" "LB_NO_GRAPH=1" "LB_GEGLU_TILE=256" "LB_NO_GRAPH=1 LB_NO_PDL=1" "LB_NO_GRAPH=1 LB_NO_LN_FOLD=1"; do
+  for e in "" "LB_NO_GRAPH=1" "LB_LN_FOLD=1" "LB_LN_FOLD=1 LB_NO_GRAPH=1" ${AB_EXTRA:-}; do
     env $e timeout 300 python tools/time_unet_batch.py 2 >> $O/ab.txt 2>&1
   done
   cat $O/ab.txt ;;
 dual2)
-  for e in "" "LB_NO_GRAPH=1" "LB_NO_GRAPH=1 LB_NO_PDL=1"; do
+  for e in "" "LB_NO_GRAPH=1"; do
     echo "== env: $e" >> $O/dual2.txt; env $e timeout 300 python tools/time_dual_stream.py >> $O/dual2.txt 2>&1
   done
   cat $O/dual2.txt ;;
