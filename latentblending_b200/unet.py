@@ -405,10 +405,12 @@ class UNetB200:
         self._plans = {}
 
     # -- public -----------------------------------------------------------------------------
-    def plan(self, B, H, W):
-        key = (B, H, W)
+    def plan(self, B, H, W, tag=None, x_in=None):
+        """The lowered program for (batch, height, width).  ``tag`` keeps several independent instances (own
+        activation buffers) of the same shape apart; ``x_in`` lets the caller supply the input buffer."""
+        key = (B, H, W) if tag is None else (B, H, W, tag)
         if key not in self._plans:
-            self._plans[key] = _Lowering(self, B, H, W)
+            self._plans[key] = _Lowering(self, B, H, W, x_in=x_in)
         return self._plans[key]
 
     @torch.no_grad()
@@ -431,7 +433,7 @@ class UNetB200:
 
 
 class _Lowering:
-    def __init__(self, net: UNetB200, B, H, W):
+    def __init__(self, net: UNetB200, B, H, W, x_in=None):
         cfg, Wt = net.cfg, net.packed.w
         self.net, self.B, self.H, self.W = net, B, H, W
         dev = net.device
@@ -441,7 +443,9 @@ class _Lowering:
         assert H % (1 << (L - 1)) == 0 and W % (1 << (L - 1)) == 0, "latent size must be divisible by 2^(levels-1)"
         T = cfg.time_embed_dim
         groups = cfg.norm_num_groups
-        self.x_in = torch.zeros(B, cfg.in_channels, H, W, **f16)
+        if x_in is not None:
+            assert tuple(x_in.shape) == (B, cfg.in_channels, H, W) and x_in.dtype == torch.float16 and x_in.is_contiguous()
+        self.x_in = x_in if x_in is not None else torch.zeros(B, cfg.in_channels, H, W, **f16)
         self.eps = torch.zeros(B, cfg.out_channels, H, W, **f16)
         self.ctx = torch.zeros(B * 77, cfg.cross_attention_dim, **f16)
         self.text = torch.zeros(B, cfg.pooled_dim, **f16)

@@ -325,3 +325,32 @@ def test_lockstep_speculation_builds_the_sequential_tree(turbo):
     assert b[4]["used"] == len(a[0]) - 2 - (0 if turbo else sum(1 for s in be.list_nmb_stems if int(s) == 1))
     assert b[4]["rounds"] < b[4]["used"]                 # speculation saved rounds
     print("speculation stats", b[4])
+
+
+def test_dual_stream_cfg_halves_are_bit_identical_to_the_batch2_program():
+    """DiffusersHolder.dual_stream: the unconditional and the text half of a branch as two batch-1 programs on two
+    CUDA streams.  Batch-invariant kernels -> the trajectory equals the single batch-2 program's bit for bit, also
+    with an in-loop crossfeed mix (which breaks the fused next-step scale) and from a mid-trajectory restart."""
+    from latentblending_b200 import DiffusersHolder
+    _, pp, _ = _pair(False, seed=2)
+    dh = DiffusersHolder(pp)
+    dh.guidance_scale = 3.5
+    dh.set_dimensions((256, 128))
+    dh.set_num_inference_steps(6)
+    emb = dh.get_text_embedding("a lake")
+    start = dh.get_noise(5)
+    other = dh.run_diffusion_sd_xl(emb, dh.get_noise(6))
+    coeffs = [0.0, 0.4, 0.0, 0.3, 0.0, 0.0]
+    res = {}
+    for dual in (False, True):
+        dh.dual_stream = dual
+        a = dh.run_diffusion_sd_xl(emb, start)
+        b = dh.run_diffusion_sd_xl(emb, start, 0, other, coeffs)
+        c = dh.run_diffusion_sd_xl(emb, a[2], idx_start=3)
+        torch.cuda.synchronize()
+        res[dual] = [t.clone() for t in a] + [t.clone() for t in b] + [t.clone() for t in c[3:]]
+    assert len(res[True]) == len(res[False]) == 15
+    for i, (x, y) in enumerate(zip(res[True], res[False])):
+        assert torch.equal(x, y), i
+    from latentblending_b200 import ops
+    assert ops.error_flag() == 0
