@@ -506,7 +506,8 @@ def run_ours(args):
                              traffic=tr.get("mix", {}).get("dram_bytes_per_launch"),
                              traffic_source=tr.get("mix", {}).get("source")))
 
-    par = "single GPU" if world == 1 else f"branch-sharded x{world} (CFG halves split over GPU pairs when stems < ranks)"
+    par = "single GPU" if world == 1 else (f"branch-sharded x{world}: one speculative candidate per rank, CFG halves "
+                                           f"split over GPU pairs for the outer trajectories (>= 4 ranks) and the last stems of a level")
     wc = workload_config(cfg, par)
     wc["stems"] = stems_run
     wc["speculative_batch"] = be._speculation_width() if world == 1 else 1

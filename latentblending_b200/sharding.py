@@ -28,7 +28,8 @@ guidance every UNet forward is a batch of two (unconditional, text).  When there
 useful candidates the ranks pair up into TEAMS of two: each team computes ONE candidate, each member one
 CFG half (a batch-1 forward, ~0.6x the time of the batch-2 one), and the two 128 KB eps halves are
 exchanged once per step inside the team (DiffusersHolder.cfg_split).  The per-round all-gather then takes
-each team's slab from its first member.
+each team's slab from its first member.  Pairs shorten the dependent chain but halve the candidates per round, so
+they are used for the outer trajectories (from 4 ranks) and for the last stems of a level (``team_size``).
 
 This module is pure host logic + collectives; the arithmetic is injected (``compute``,
 ``similarity``), which is how the world_size-2 gloo test drives it on CPU.
@@ -96,14 +97,14 @@ class LevelSharder:
 
     # -- teams ---------------------------------------------------------------------------------
     def team_size(self, remaining):
-        """Ranks per candidate this round.  Pairs (one CFG half per rank: a batch-1 forward costs ~0.6x a batch-2 one)
-        whenever the ranks outnumber what speculation can use: always from 4 ranks up (levels have few stems and the
-        hit rate of the 3rd, 4th, ... speculative candidate is low), and on 2 ranks for the last stem of a level."""
+        """Ranks per candidate this round.  A pair (one CFG half per rank) shortens the dependent chain -- a batch-1
+        forward is ~0.72x a batch-2 one (15.7 vs 21.7 ms @128x128, r02d) -- but halves the number of speculative
+        candidates per round, and a missed pick costs a whole extra round.  So pairs are used when single ranks could
+        not be put to use anyway: for the last stem of a level, and whenever the ranks outnumber the remaining stems
+        four to one (8 ranks: remaining <= 2; then the world // 2 pair-teams still cover the likely picks)."""
         if not self.cfg_pairs:
             return 1
-        if self.world >= 4:
-            return 2
-        return 2 if remaining <= 1 else 1
+        return 2 if (remaining <= 1 or 4 * remaining <= self.world) else 1
 
     def pair_group(self):
         """The 2-rank process group of this rank's team; all groups are created collectively on first use."""

@@ -148,7 +148,7 @@ def test_sharded_tree_equals_sequential(world, levels, pairs):
     # speculation can only save rounds, never add any
     assert results[0][5]["rounds"] <= sum(s for _, s in levels)
     if pairs and world == 4:
-        assert results[0][5]["paired_rounds"] == results[0][5]["rounds"]      # 4 ranks: always two teams of two
+        assert 1 <= results[0][5]["paired_rounds"] <= results[0][5]["rounds"]   # pairs for the last stem(s) of a level
     print("rounds", results[0][5]["rounds"], "of", sum(s for _, s in levels), "branches; computed",
           results[0][5]["computed"])
 
