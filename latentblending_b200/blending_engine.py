@@ -69,9 +69,12 @@ class BlendingEngine():
         self.output_device_frames = False     # True: run_transition returns uint8 device frames, no D2H / PIL
         self.batch_outer_pair = True          # the two outer trajectories share batch-4 UNet forwards (same results)
         # single-GPU speculation width: candidate branches of a level advanced in lockstep through ONE batched UNet
-        # forward (sharding.run_level_local).  None = by model: SDXL-Turbo 512^2 (weight-bandwidth / launch bound,
-        # a batch-4 forward costs about one batch-1 forward) -> 4; SDXL base 1024^2 -> 1 (batch 4 costs 1.76x batch 2)
+        # forward (sharding.run_level_local).  None = by model: SDXL-Turbo 512^2 (weight-bandwidth / launch bound, a
+        # batch-4 forward costs about one batch-1 forward) -> 4; SDXL base 1024^2 -> 2 (a batch-4 forward costs 1.78x a
+        # batch-2 one, r02d: worth it while >= 78 % of the second candidates end up in the tree -- the running hit rate
+        # is tracked and the width drops to 1 below that; 13 of 13 on the bench workload, r02e shard stats).
         self.speculative_batch = None
+        self._spec_hits = [0, 0]            # second-or-later candidates: [used, computed], over the engine's lifetime
         # ancestral-scheduler noise per (seeds, branch position, step) from its own generator instead of the global
         # RNG: results then do not depend on the order branches are computed in (speculation, multi-GPU sharding)
         self.deterministic_noise = False
@@ -236,15 +239,20 @@ class BlendingEngine():
         # matters for the first argmax, so a placeholder keeps the same behaviour
         self.tree_similarities = [None]
 
-        width = self._speculation_width()
         self.spec_stats = dict(rounds=0, computed=0, used=0)
         for s_idx in range(len(self.list_idx_injection)):
             nmb_stems = int(self.list_nmb_stems[s_idx])
             idx_injection = int(self.list_idx_injection[s_idx])
+            width = self._speculation_width()
             if width > 1 and nmb_stems > 1:
                 from .sharding import run_level_local
+                before = dict(self.spec_stats)
                 run_level_local(self, idx_injection, nmb_stems, self._compute_candidates, self.get_lpips_similarity,
                                 width, on_insert=self.set_guidance_mid_dampening, stats=self.spec_stats)
+                rounds = self.spec_stats["rounds"] - before["rounds"]
+                # every round's first candidate is the reference's own next pick; the others are the speculation
+                self._spec_hits[0] += (self.spec_stats["used"] - before["used"]) - rounds
+                self._spec_hits[1] += (self.spec_stats["computed"] - before["computed"]) - rounds
                 continue
             for _ in range(nmb_stems):
                 fract_mixing, b_parent1, b_parent2 = self.get_mixing_parameters(idx_injection)
@@ -258,7 +266,10 @@ class BlendingEngine():
             return 1
         if self.speculative_batch is not None:
             return max(1, int(self.speculative_batch))
-        return 4 if self.dh.is_sdxl_turbo else 1
+        if self.dh.is_sdxl_turbo:
+            return 4
+        used, computed = self._spec_hits
+        return 2 if (computed < 4 or used >= 0.78 * computed) else 1
 
     def _guidance_for(self, fract_mixing):
         """set_guidance_mid_dampening's value without touching the engine / holder state."""

@@ -259,8 +259,11 @@ def test_unforced_transition_places_branches_like_the_oracle_while_margins_allow
     op, pp, lp = _pair(False, seed=7)
     oe = OracleEngine(OracleHolder(op), lpips_net=lp)
     be = BlendingEngine(pp, run_benchmark=False)
-    be.dh.get_noise = lambda seed: oe.dh.get_noise(seed).cuda()
-    for e in (oe, be):
+    be2 = BlendingEngine(pp, run_benchmark=False)        # same, with the default lockstep speculation (width 2)
+    be.speculative_batch = 1                             # strictly sequential: insert_into_tree sees every branch
+    for b in (be, be2):
+        b.dh.get_noise = lambda seed: oe.dh.get_noise(seed).cuda()
+    for e in (oe, be, be2):
         e.set_dimensions((128, 128))
         e.set_num_inference_steps(8)
         e.set_prompt1("photo of a lake")
@@ -295,6 +298,12 @@ def test_unforced_transition_places_branches_like_the_oracle_while_margins_allow
     print(f"unforced transition: {compared}/{len(order_o)} decisions above the 10 % margin, all equal; margins "
           f"{[round(m, 3) for m in margins]}")
     assert compared >= 1
+    # the default engine (speculation width 2 for SDXL base) builds the very same tree, bit for bit
+    be2.run_transition(fixed_seeds=[420, 421])
+    assert be2._speculation_width() >= 1 and be2.spec_stats["computed"] >= be2.spec_stats["used"] > 0
+    assert be2.tree_fracts == be.tree_fracts and [float(v) for v in be2.tree_similarities] == [float(v) for v in be.tree_similarities]
+    for ta, tb in zip(be2.tree_latents, be.tree_latents):
+        assert torch.equal(ta[-1], tb[-1])
 
 
 @pytest.mark.parametrize("turbo", [False, True])
