@@ -512,7 +512,7 @@ def run_ours(args):
     wc["stems"] = stems_run
     wc["speculative_batch"] = be._speculation_width() if world == 1 else 1
     if getattr(be, "spec_stats", None) and world == 1:
-        wc["speculation"] = dict(be.spec_stats)
+        wc["speculation"] = dict(be.spec_stats, lifetime_second_candidates_used_of_computed=list(be._spec_hits))
     if args.config == 4:
         wc.update(frames=frames // max(1, args.steps), t_compute_max_allowed=args.t_compute,
                   dt_unet_step=round(float(be.dt_unet_step), 5), dt_vae=round(float(be.dt_vae), 5))

@@ -247,8 +247,12 @@ class BlendingEngine():
             if width > 1 and nmb_stems > 1:
                 from .sharding import run_level_local
                 before = dict(self.spec_stats)
-                run_level_local(self, idx_injection, nmb_stems, self._compute_candidates, self.get_lpips_similarity,
-                                width, on_insert=self.set_guidance_mid_dampening, stats=self.spec_stats)
+                # the half-gap similarity estimate (split_ratio) keeps adapting across levels and transitions, like the
+                # sharder's: it orders the speculative candidates
+                self._split_ratio = run_level_local(
+                    self, idx_injection, nmb_stems, self._compute_candidates, self.get_lpips_similarity, width,
+                    on_insert=self.set_guidance_mid_dampening, stats=self.spec_stats,
+                    split_ratio=getattr(self, "_split_ratio", 0.6))
                 rounds = self.spec_stats["rounds"] - before["rounds"]
                 # every round's first candidate is the reference's own next pick; the others are the speculation
                 self._spec_hits[0] += (self.spec_stats["used"] - before["used"]) - rounds

@@ -69,5 +69,24 @@ def main():
                                   tflops=round(fl / t / 1e12, 1))))
 
 
+def vae_shapes():
+    """The big 3x3 convolutions of the SDXL VAE decoder at 1024^2 output (batch 1)."""
+    for name, hw, cin, cout in (("vae_up3_128", 1024, 128, 128), ("vae_upconv_256", 1024, 256, 256),
+                                ("vae_up2_256", 512, 256, 256), ("vae_upconv_512", 512, 512, 512),
+                                ("vae_up1_512", 256, 512, 512), ("vae_up0_512", 128, 512, 512)):
+        M = hw * hw
+        a = torch.randn(M, cin, device="cuda").half()
+        w = (torch.randn(cout, 9 * cin, device="cuda") * 0.02).half()
+        out = torch.empty(M, cout, device="cuda", dtype=torch.float16)
+        t = time_it(lambda: ops.gemm(a, w, cout, 1, hw, hw, taps=9, out=out, static_w=True), iters=5, warm=2)
+        fl = 2 * M * cout * 9 * cin
+        print(json.dumps(dict(op="conv3x3", name=name, M=M, N=cout, K=9 * cin, us=round(t * 1e6, 1),
+                              tflops=round(fl / t / 1e12, 1), cluster=os.environ.get("LB_GEMM_CLUSTER", "auto"))))
+        del a, w, out
+
+
 if __name__ == "__main__":
-    main()
+    if "vae" in sys.argv[1:]:
+        vae_shapes()
+    else:
+        main()

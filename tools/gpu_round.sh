@@ -43,6 +43,10 @@ small)
 ncu_small)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gn_|ln_kernel|cfg_euler|scale_input|embed_inputs" -c 24 -o $O/small -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_small.py > $O/ncu_small.log 2>&1; echo "ncu small exit $?" ;;
+vaeconv)
+  : > $O/bench_vae_conv.txt
+  for c in "" "LB_GEMM_CLUSTER=1" "LB_GEMM_CLUSTER=2"; do env $c timeout 300 python tools/bench_ops.py vae >> $O/bench_vae_conv.txt 2>&1; done
+  cat $O/bench_vae_conv.txt ;;
 cluster2)
   LB_GEMM_CLUSTER=2 timeout 300 python tools/bench_ops.py gemm > $O/bench_ops_cluster2.txt 2>&1; cat $O/bench_ops_cluster2.txt ;;
 dual)
