@@ -662,7 +662,11 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
     // (measured: the pair wins ~3 % on long-K multi-wave problems -- the big convolutions -- and loses up to 15 %
     //  on short-K / single-wave ones, where its cluster launch + sync overhead dominates)
     const char* force = getenv("LB_GEMM_CLUSTER");
-    plan->cluster = (p.tiles_m >= 2 && total >= 40 && (int64_t)p.tiles_m * p.tiles_n >= 256) ? 2 : 1;
+    // (r02g: the pair also wins 7-13 % on the huge-M, N <= 256 VAE-decoder convolutions -- 1M x 128 x 1152 308 -> 287 us,
+    //  1M x 256 x 2304 941 -> 836 us, 262144 x 256 x 2304 232 -> 209 us: thousands of tiles, the shared weight tile halves
+    //  each SM's operand traffic -- even though their K is short)
+    const int64_t n_tiles = (int64_t)p.tiles_m * p.tiles_n;
+    plan->cluster = (p.tiles_m >= 2 && n_tiles >= 256 && (total >= 40 || (p.tiles_m >= 256 && n_tiles >= 1024))) ? 2 : 1;
     if (force) plan->cluster = (atoi(force) == 2 && p.tiles_m >= 2) ? 2 : 1;
     if (plan->cluster == 2) {
         const int groups = ((p.tiles_m + 1) / 2) * p.tiles_n;
