@@ -24,6 +24,8 @@
 // Bound: tensor pipe / MUFU.EX2 (16/clk/SM): at head dim 64 one exp feeds only 256 tensor FLOPs, so MUFU alone caps
 // the tensor pipe at 50 %; every 4th pair of exps runs as a packed-fp32 polynomial on the FMA pipe instead.
 // Algorithmic FLOPs = 4*Sq*Skv*64 per head.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -53,6 +55,9 @@ constexpr uint32_t kTmemCols = 512;             // S0 [0,128) S1 [128,256) O0 [2
 //   softmax WG0:  -------- softmax(S0[j]) ------ | softmax(S0[j+1]) ...
 //   softmax WG1:       -------- softmax(S1[j]) ------ | ...
 // Each half's softmax overlaps the other half's MMAs; K/V tiles are loaded once per 256 query rows.
+// kPolyMask: which of the 4 exp pairs of every 8-column group take the packed-fp32 polynomial 2^x on the FMA pipe instead
+// of MUFU.EX2 (bit i = pair i).  0b1000 = every 4th pair (round 1); 0b1010 = every 2nd pair.
+template <int kPolyMask>
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
                         const float2 x2 = ffma2(make_float2(__uint_as_float(cur[g * 8 + 2 * i]),
                                                             __uint_as_float(cur[g * 8 + 2 * i + 1])), sc2, nm2);
                         float2 e2;
-                        if (i == 3) {
+                        if ((kPolyMask >> i) & 1) {
                             e2 = ex2_poly2(x2);
                         } else {
                             e2.x = ex2_approx(x2.x);
@@ -399,15 +404,26 @@ int attn_plan_build(lb_ctx* ctx, const lb_attn_desc& d, AttnPlan* plan) {
     return 0;
 }
 
-int attn_plan_launch(const AttnPlan& plan, cudaStream_t st) {
+template <int kPolyMask> static int attn_launch_variant(const AttnPlan& plan, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        LB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        LB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kPolyMask>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         attr_set = true;
     }
-    lb_launch_pdl(attn_tc_kernel, plan.grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, plan.p);
+    lb_launch_pdl(attn_tc_kernel<kPolyMask>, plan.grid, dim3(kAttnThreads), (size_t)kAttnSmem, st, plan.p);
     LB_LAUNCH_CHECK();
     return 0;
+}
+
+int attn_plan_launch(const AttnPlan& plan, cudaStream_t st) {
+    static int poly = -1;
+    if (poly < 0) poly = getenv("LB_ATTN_POLY") ? atoi(getenv("LB_ATTN_POLY")) : 8;
+    switch (poly) {
+        case 0: return attn_launch_variant<0>(plan, st);        // all exps on MUFU.EX2
+        case 10: return attn_launch_variant<10>(plan, st);      // every 2nd pair on the FMA pipe
+        case 14: return attn_launch_variant<14>(plan, st);      // three of four pairs on the FMA pipe
+        default: return attn_launch_variant<8>(plan, st);       // every 4th pair (default)
+    }
 }
 
 extern "C" int lb_attention(lb_ctx* ctx, const lb_attn_desc* desc, void* stream) {

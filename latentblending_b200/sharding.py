@@ -99,12 +99,14 @@ class LevelSharder:
     def team_size(self, remaining):
         """Ranks per candidate this round.  A pair (one CFG half per rank) shortens the dependent chain -- a batch-1
         forward is ~0.72x a batch-2 one (15.7 vs 21.7 ms @128x128, r02d) -- but halves the number of speculative
-        candidates per round, and a missed pick costs a whole extra round.  So pairs are used when single ranks could
-        not be put to use anyway: for the last stem of a level, and whenever the ranks outnumber the remaining stems
-        four to one (8 ranks: remaining <= 2; then the world // 2 pair-teams still cover the likely picks)."""
+        candidates per round, and a missed pick costs a whole extra round.  So pairs are used when the pair-teams still
+        cover every remaining stem of the level (world // 2 >= remaining: all levels of the 15-branch tree on 8 ranks,
+        the 2- and 1-stem levels on 4 ranks) and for the last stem of a level.  Measured on 4 ranks (r02h): one
+        candidate per rank already finishes every level of the bench tree in ONE round, so more single-rank candidates
+        cannot help 8 ranks -- shorter steps can."""
         if not self.cfg_pairs:
             return 1
-        return 2 if (remaining <= 1 or 4 * remaining <= self.world) else 1
+        return 2 if (remaining <= 1 or self.world // 2 >= remaining) else 1
 
     def pair_group(self):
         """The 2-rank process group of this rank's team; all groups are created collectively on first use."""

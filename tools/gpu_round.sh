@@ -43,6 +43,10 @@ small)
 ncu_small)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gn_|ln_kernel|cfg_euler|scale_input|embed_inputs" -c 24 -o $O/small -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_small.py > $O/ncu_small.log 2>&1; echo "ncu small exit $?" ;;
+attnpoly)
+  : > $O/attn_poly.txt
+  for v in 8 0 10 14; do echo "== LB_ATTN_POLY=$v" >> $O/attn_poly.txt; LB_ATTN_POLY=$v timeout 200 python tools/bench_ops.py attn >> $O/attn_poly.txt 2>&1; done
+  cat $O/attn_poly.txt ;;
 vaeconv)
   : > $O/bench_vae_conv.txt
   for c in "" "LB_GEMM_CLUSTER=1" "LB_GEMM_CLUSTER=2"; do env $c timeout 300 python tools/bench_ops.py vae >> $O/bench_vae_conv.txt 2>&1; done
