@@ -43,6 +43,11 @@ small)
 ncu_small)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gn_|ln_kernel|cfg_euler|scale_input|embed_inputs" -c 24 -o $O/small -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_small.py > $O/ncu_small.log 2>&1; echo "ncu small exit $?" ;;
+configs)
+  for c in 3 5 4; do
+    timeout 900 python bench.py --config $c --steps ${CFG_STEPS:-2} --warmup ${CFG_WARM:-1} --no-cpu-baseline > $O/bench_config$c.json 2> $O/bench_config$c.err
+    echo "config $c exit $?"; cut -c1-900 $O/bench_config$c.json; tail -2 $O/bench_config$c.err
+  done ;;
 attnpoly)
   : > $O/attn_poly.txt
   for v in 8 0 10 14; do echo "== LB_ATTN_POLY=$v" >> $O/attn_poly.txt; LB_ATTN_POLY=$v timeout 200 python tools/bench_ops.py attn >> $O/attn_poly.txt 2>&1; done
