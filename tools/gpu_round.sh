@@ -43,6 +43,10 @@ small)
 ncu_small)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gn_|ln_kernel|cfg_euler|scale_input|embed_inputs" -c 24 -o $O/small -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_small.py > $O/ncu_small.log 2>&1; echo "ncu small exit $?" ;;
+vaeprof)
+  timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+     --log-file $O/vae_launches.csv python tools/profile_vae.py > $O/vae_launches.log 2>&1; echo "vae launches exit $?"; cat $O/vae_launches.log | tail -2
+  LB_NO_GRAPH=0 timeout 300 python tools/profile_vae.py > $O/vae_time.txt 2>&1; cat $O/vae_time.txt ;;
 configs)
   for c in 3 5 4; do
     timeout 900 python bench.py --config $c --steps ${CFG_STEPS:-2} --warmup ${CFG_WARM:-1} --no-cpu-baseline > $O/bench_config$c.json 2> $O/bench_config$c.err
