@@ -43,6 +43,9 @@ small)
 ncu_small)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gn_|ln_kernel|cfg_euler|scale_input|embed_inputs" -c 24 -o $O/small -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_small.py > $O/ncu_small.log 2>&1; echo "ncu small exit $?" ;;
+ncu_attn)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_tc -c 2 -o $O/attn -f \
+     env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_ops.py attn > $O/ncu_attn.log 2>&1; echo "ncu attn exit $?" ;;
 vaeprof)
   timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
      --log-file $O/vae_launches.csv python tools/profile_vae.py > $O/vae_launches.log 2>&1; echo "vae launches exit $?"; cat $O/vae_launches.log | tail -2
