@@ -214,6 +214,11 @@ int lb_softmax_rows(lb_ctx* ctx, const void* x, int64_t ld, int64_t rows, int co
                     void* stream);
 int lb_postprocess_u8(lb_ctx* ctx, const void* img_nchw, int B, int C, int64_t hw, void* out_u8_nhwc,
                       int* nonfinite_count_dev, void* stream);
+/* lb_nhwc_to_nchw: the first C (<= 8) columns of NHWC rows [B*hw, ld] -> NCHW [B, C, hw].  The C0 -> 4 (UNet eps) and
+ * C0 -> 3 (VAE RGB) output convolutions run as lb_gemm with an 8-row zero-padded weight matrix (N = 8); this puts the
+ * result back into the reference's [B,C,H,W] tensor layout.  (lb_conv_out is the direct kernel for widths that are not
+ * multiples of 64.) */
+int lb_nhwc_to_nchw(lb_ctx* ctx, const void* x, int64_t ld, int B, int C, int64_t hw, void* out_nchw, void* stream);
 
 /* ---- LPIPS-AlexNet branch-placement metric (blending_engine.py:744-758, lpips==0.1.4) ----
  * The five AlexNet convolutions run on lb_gemm (LB_GEMM_RELU) over patch matrices:
@@ -254,7 +259,7 @@ enum {
     LB_OP_GEMM = 1, LB_OP_ATTENTION = 2, LB_OP_GROUPNORM = 3, LB_OP_LAYERNORM = 4, LB_OP_EMBED_INPUTS = 5,
     LB_OP_LINEAR_SMALL = 6, LB_OP_CONV_IN = 7, LB_OP_CONV_OUT = 8, LB_OP_UPSAMPLE2X = 9, LB_OP_IM2COL_S2 = 10,
     LB_OP_LATENT_PREP = 11, LB_OP_SOFTMAX_ROWS = 12, LB_OP_POSTPROCESS_U8 = 13,
-    LB_OP_LPIPS_IM2COL_U8 = 14, LB_OP_IM2COL = 15, LB_OP_MAXPOOL3S2 = 16
+    LB_OP_LPIPS_IM2COL_U8 = 14, LB_OP_IM2COL = 15, LB_OP_MAXPOOL3S2 = 16, LB_OP_NHWC_TO_NCHW = 17
 };
 typedef struct lb_op {
     int32_t kind;
@@ -273,7 +278,8 @@ typedef struct lb_op {
                  int32_t Cout; void* out; int64_t ld_out; } conv;
         struct { const void* x; int64_t ld_x; int32_t B, H, W, C; void* out; int64_t ld_out; } resample;
         /* LATENT_PREP: x,w,bias,out,B,C,n=h*w; SOFTMAX_ROWS: x,ld_x,out,ld_out,n=rows,C=cols;
-         * POSTPROCESS_U8: x,out,B,C,n=h*w, w = optional device int counter of non-finite pixels */
+         * POSTPROCESS_U8: x,out,B,C,n=h*w, w = optional device int counter of non-finite pixels;
+         * NHWC_TO_NCHW: x,ld_x,out,B,C,n=h*w */
         struct { const void* x; int64_t ld_x; const void* w; const void* bias; void* out; int64_t ld_out;
                  int64_t n; int32_t B, C; } aux;
         /* LPIPS_IM2COL_U8 (x = uint8 frame, C = out_cols, f = shift[3], scale[3]); IM2COL; MAXPOOL3S2 (k/stride/pad unused) */

@@ -464,6 +464,21 @@ softmax_rows_kernel(const __half* __restrict__ x, long long ld, int cols, __half
     }
 }
 
+// NHWC rows [B*hw, ld] (first C columns) -> NCHW [B, C, hw]: the boundary of the conv_out GEMM (C = 4 eps / 3 RGB
+// channels out of an 8-column accumulator tile) back to the reference's tensor layout.
+__global__ void __launch_bounds__(kThreads)
+nhwc_to_nchw_kernel(const __half* __restrict__ x, long long ld, int B, int C, long long hw, __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long total = (long long)B * hw;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const long long b = i / hw, p = i % hw;
+        const uint4 v = *reinterpret_cast<const uint4*>(x + i * ld);       // 8 channels of this pixel
+        const __half* h = reinterpret_cast<const __half*>(&v);
+        for (int c = 0; c < C; ++c) out[(b * C + c) * hw + p] = h[c];
+    }
+}
+
 // VaeImageProcessor.postprocess: NCHW fp16 image -> uint8 NHWC, (x/2+0.5).clamp(0,1)*255 rounded half-to-even.
 // `nonfinite` (optional) counts NaN/Inf pixels: the decoder runs in fp16 where the reference upcasts the stock SDXL VAE
 // to fp32 ("overflows in float16", diffusers_holder.py:128); an overflow anywhere upstream reaches the image as Inf/NaN.
@@ -508,6 +523,17 @@ extern "C" int lb_softmax_rows(lb_ctx* ctx, const void* x, int64_t ld, int64_t r
     LB_REQUIRE(rows <= 2147483647LL, "lb_softmax_rows: too many rows");
     if (rows == 0) return 0;
     lb_launch_pdl(softmax_rows_kernel, (unsigned)rows, kThreads, 0, lb_stream(stream), (const __half*)x, ld, cols, (__half*)out, ldo);
+    LB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lb_nhwc_to_nchw(lb_ctx* ctx, const void* x, int64_t ld, int B, int C, int64_t hw, void* out_nchw,
+                               void* stream) {
+    LB_REQUIRE(ctx && x && out_nchw, "lb_nhwc_to_nchw: null argument");
+    LB_REQUIRE(C >= 1 && C <= 8 && ld % 8 == 0 && ld >= 8 && lb_aligned16(x), "lb_nhwc_to_nchw: C <= 8, row stride a "
+               "multiple of 8 elements, 16B aligned base");
+    lb_launch_pdl(nhwc_to_nchw_kernel, grid_for((long long)B * hw, ctx->sm_count), kThreads, 0, lb_stream(stream),
+                  (const __half*)x, (long long)ld, B, C, (long long)hw, (__half*)out_nchw);
     LB_LAUNCH_CHECK();
     return 0;
 }

@@ -66,7 +66,7 @@ extern "C" int lb_program_create(lb_ctx* ctx, const lb_op* ops, int64_t n_ops, l
             case LB_OP_EMBED_INPUTS: case LB_OP_LINEAR_SMALL: case LB_OP_CONV_IN: case LB_OP_CONV_OUT:
             case LB_OP_UPSAMPLE2X: case LB_OP_IM2COL_S2: case LB_OP_GROUPNORM: case LB_OP_LAYERNORM:
             case LB_OP_LATENT_PREP: case LB_OP_SOFTMAX_ROWS: case LB_OP_POSTPROCESS_U8:
-            case LB_OP_LPIPS_IM2COL_U8: case LB_OP_IM2COL: case LB_OP_MAXPOOL3S2:
+            case LB_OP_LPIPS_IM2COL_U8: case LB_OP_IM2COL: case LB_OP_MAXPOOL3S2: case LB_OP_NHWC_TO_NCHW:
                 break;
             default:
                 lb_set_error("lb_program_create: op %lld has unknown kind %d", (long long)i, ops[i].kind);
@@ -227,6 +227,11 @@ static int program_launch_all(lb_program* prog, float t, const float* t_dev, uin
             case LB_OP_POSTPROCESS_U8: {
                 const auto& a = o.u.aux;
                 e = lb_postprocess_u8(ctx, a.x, a.B, a.C, a.n, a.out, (int*)const_cast<void*>(a.w), stream);
+                break;
+            }
+            case LB_OP_NHWC_TO_NCHW: {
+                const auto& a = o.u.aux;
+                e = lb_nhwc_to_nchw(ctx, a.x, a.ld_x, a.B, a.C, a.n, a.out, stream);
                 break;
             }
             case LB_OP_LPIPS_IM2COL_U8: {

@@ -20,6 +20,7 @@ Data layout in HBM (all fp16):
   * latents / eps stay NCHW [B,4,h,w] like the reference's tensors.
 """
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Tuple
 
@@ -28,7 +29,7 @@ import torch
 from . import _cabi
 from ._cabi import (GEMM_GEGLU256, GEMM_RELU, GEMM_STATIC_W, OP_ATTENTION, OP_CONV_IN, OP_CONV_OUT, OP_EMBED_INPUTS, OP_GEMM,
                     OP_GROUPNORM, OP_IM2COL, OP_IM2COL_S2, OP_LATENT_PREP, OP_LAYERNORM, OP_LINEAR_SMALL,
-                    OP_LPIPS_IM2COL_U8, OP_MAXPOOL3S2, OP_POSTPROCESS_U8, OP_SOFTMAX_ROWS, OP_UPSAMPLE2X, Op, check, ctx,
+                    OP_LPIPS_IM2COL_U8, OP_MAXPOOL3S2, OP_NHWC_TO_NCHW, OP_POSTPROCESS_U8, OP_SOFTMAX_ROWS, OP_UPSAMPLE2X, Op, check, ctx,
                     stream_ptr)
 
 
@@ -190,6 +191,14 @@ class Program:
         d.w, d.bias, d.Cout, d.out = _p(w), _p(bias), Cout, _p(out_nchw)
         self.hold(x, w, bias, out_nchw)
 
+    def conv_out_gemm(self, x, B, H, W, Cin, w8, bias8, Cout, out_nchw, tmp):
+        """The C0 -> Cout (<= 8) 3x3 output convolution on the tensor-core GEMM: N = 8 (zero-padded weight rows),
+        then the Cout live columns go back to NCHW.  ``tmp``: [B*H*W, 8] fp16 scratch."""
+        self.gemm(x, w8, 8, B, H, W, tmp, taps=9, a0_c=Cin, bias=bias8)
+        d = self._new(OP_NHWC_TO_NCHW).u.aux
+        d.x, d.ld_x, d.out, d.n, d.B, d.C = _p(tmp), tmp.stride(0), _p(out_nchw), H * W, B, Cout
+        self.hold(tmp, out_nchw)
+
     def upsample2x(self, x, B, H, W, C, out):
         d = self._new(OP_UPSAMPLE2X).u.resample
         d.x, d.ld_x, d.B, d.H, d.W, d.C, d.out, d.ld_out = _p(x), x.stride(0), B, H, W, C, _p(out), out.stride(0)
@@ -268,6 +277,19 @@ class Program:
             pass
 
 
+def pack_conv_out8(w_co_ky_kx_ci, bias):
+    """[Cout<=8][3][3][Cin] conv_out weights -> ([8, 9*Cin] zero-padded rows, [8] bias) for the N = 8 GEMM; None when
+    Cin is not a multiple of 64 (the GEMM's K blocks) -- the direct lb_conv_out kernel is used then."""
+    co, cin = w_co_ky_kx_ci.shape[0], w_co_ky_kx_ci.shape[-1]
+    if cin % 64 != 0 or co > 8:
+        return None, None
+    w8 = torch.zeros(8, 9 * cin, dtype=torch.float16, device=w_co_ky_kx_ci.device)
+    w8[:co] = w_co_ky_kx_ci.reshape(co, 9 * cin)
+    b8 = torch.zeros(8, dtype=torch.float16, device=bias.device)
+    b8[:co] = bias
+    return w8.contiguous(), b8.contiguous()
+
+
 def _fold_layernorm(w, bias, gamma, beta):
     """(w*gamma in fp16, rowsum of THAT in fp32, w beta + bias in fp32) for the LayerNorm-folded GEMM."""
     wf = (w.float() * gamma.float()[None, :]).half().contiguous()
@@ -309,6 +331,7 @@ class PackedUNet:
         W["conv_in.b"] = g("conv_in.bias")
         W["conv_out.w"] = g("conv_out.weight").permute(0, 2, 3, 1).contiguous()     # [co][ky][kx][Cin]
         W["conv_out.b"] = g("conv_out.bias")
+        W["conv_out.w8"], W["conv_out.b8"] = pack_conv_out8(W["conv_out.w"], W["conv_out.b"])
         for nm in ("conv_norm_out",):
             W[nm + ".g"], W[nm + ".b"] = g(nm + ".weight"), g(nm + ".bias")
         for e in ("time_embedding", "add_embedding"):
@@ -662,6 +685,10 @@ class _Lowering:
         # ---- out ----------------------------------------------------------------------------
         no = scratch("n1", rows_at(0), ch[0])
         P.groupnorm(x, B, H * W, ch[0], groups, Wt["conv_norm_out.g"], Wt["conv_norm_out.b"], 1e-5, 1, no, self.ws)
-        P.conv_out(no, B, H, W, ch[0], Wt["conv_out.w"], Wt["conv_out.b"], cfg.out_channels, self.eps)
+        if Wt.get("conv_out.w8") is not None and os.environ.get("LB_CONV_OUT_DIRECT") is None:
+            P.conv_out_gemm(no, B, H, W, ch[0], Wt["conv_out.w8"], Wt["conv_out.b8"], cfg.out_channels, self.eps,
+                            scratch("conv_out8", rows_at(0), 8))
+        else:
+            P.conv_out(no, B, H, W, ch[0], Wt["conv_out.w"], Wt["conv_out.b"], cfg.out_channels, self.eps)
         P.finalize()
         PC.finalize()

@@ -10,11 +10,13 @@ scores = (Wq x)(Wk x)^T (1/sqrt(C) folded into Wq), P = softmax_rows(scores), ou
 produced directly by a GEMM with swapped operands; the value bias is folded into the output bias
 (softmax rows sum to one).  Weights use the diffusers state_dict names.
 """
+import os
+
 import torch
 
 from . import _cabi
 from ._cabi import ctx
-from .unet import Program
+from .unet import Program, pack_conv_out8
 
 
 class VAEDecoderB200:
@@ -72,6 +74,7 @@ class VAEDecoderB200:
         W["norm_out.g"], W["norm_out.b"] = g("conv_norm_out.weight"), g("conv_norm_out.bias")
         W["conv_out.w"] = g("conv_out.weight").permute(0, 2, 3, 1).contiguous()
         W["conv_out.b"] = g("conv_out.bias")
+        W["conv_out.w8"], W["conv_out.b8"] = pack_conv_out8(W["conv_out.w"], W["conv_out.b"])
         self._plans = {}
         self.nonfinite = torch.zeros(1, dtype=torch.int32, device=dev)
         self.decodes_since_check = 0
@@ -186,7 +189,11 @@ class _VAELowering:
         no = sc("n1", hh * ww, cin)
         P.groupnorm(x, B, hh * ww, cin, groups, Wt["norm_out.g"], Wt["norm_out.b"], 1e-6, 1, no, self.ws)
         img = torch.empty(1, 3, hh, ww, **f16)
-        P.conv_out(no, B, hh, ww, cin, Wt["conv_out.w"], Wt["conv_out.b"], 3, img)
+        if Wt.get("conv_out.w8") is not None and os.environ.get("LB_CONV_OUT_DIRECT") is None:
+            # 14 % of a 1024^2 decode went into the direct 128 -> 3 kernel (2.07 ms, r02k); as an N = 8 GEMM it is ~0.2 ms
+            P.conv_out_gemm(no, B, hh, ww, cin, Wt["conv_out.w8"], Wt["conv_out.b8"], 3, img, sc("h1", hh * ww, 8))
+        else:
+            P.conv_out(no, B, hh, ww, cin, Wt["conv_out.w"], Wt["conv_out.b"], 3, img)
         P.postprocess_u8(img, self.frame, vae.nonfinite)
         self._keep = (scratch, z, qk, vT, scores, x2, x3, x4, img)
         P.finalize()
