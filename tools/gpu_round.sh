@@ -43,6 +43,9 @@ small)
 ncu_small)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gn_|ln_kernel|cfg_euler|scale_input|embed_inputs" -c 24 -o $O/small -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_small.py > $O/ncu_small.log 2>&1; echo "ncu small exit $?" ;;
+ncu_gemm)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 13 -o $O/gemm -f \
+     env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_ops.py gemm > $O/ncu_gemm.log 2>&1; echo "ncu gemm exit $?" ;;
 ncu_attn)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_tc -c 2 -o $O/attn -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_ops.py attn > $O/ncu_attn.log 2>&1; echo "ncu attn exit $?" ;;
