@@ -43,6 +43,11 @@ small)
 ncu_small)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gn_|ln_kernel|cfg_euler|scale_input|embed_inputs" -c 24 -o $O/small -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_small.py > $O/ncu_small.log 2>&1; echo "ncu small exit $?" ;;
+gemmsplit)
+  # which side bounds a GEMM: LB_GEMM_DEBUG=1 skips the TMA loads (MMA + epilogue only), =2 skips the MMA issue (TMA + epilogue only)
+  : > $O/gemm_split.txt
+  for d in 0 1 2; do echo "== LB_GEMM_DEBUG=$d" >> $O/gemm_split.txt; LB_GEMM_DEBUG=$d timeout 200 python tools/bench_ops.py gemm >> $O/gemm_split.txt 2>&1; done
+  cat $O/gemm_split.txt ;;
 ncu_gemm)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 13 -o $O/gemm -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_ops.py gemm > $O/ncu_gemm.log 2>&1; echo "ncu gemm exit $?" ;;
