@@ -38,8 +38,9 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kThreadsGemm = 320;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiParts = 4;                 // epilogue warps per TMEM lane quadrant (they split the tile's columns)
+constexpr int kEpiWarps = 4 * kEpiParts;     // 16
+constexpr int kThreadsGemm = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kABytes = kBM * kBK * 2;  // 16 KiB
 
 template <int BN> struct Cfg {
@@ -275,9 +276,13 @@ __global__ void __launch_bounds__(kThreadsGemm, CR ? 2 : 1) gemm_tc_kernel(const
             if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 2) {
-        // ===================== epilogue (8 warps: two per TMEM lane quadrant, splitting the columns) =====================
+        // ===================== epilogue (16 warps: four per TMEM lane quadrant, splitting the columns) =====================
+        // r02r (ncu): the GEGLU epilogue of the FF-in GEMM took ~9 900 clk per tile with 8 warps (~1 900 instructions per
+        // thread at 0.39 IPC per scheduler: two-and-a-half resident warps do not hide the FMA / TMEM latencies) against
+        // 5 120 clk of MMAs -- the tensor pipe idled half the time waiting for a free accumulator.  16 warps with 16-column
+        // chunks halve the per-warp work of every epilogue (and the exposed drain of the single-tile launches).
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int part = (warp - 2) >> 2;       // 0: first half of the tile's column chunks, 1: second half
+        const int part = (warp - 2) >> 2;       // 0..3: which quarter of the tile's 16-column chunks
         const int r = q * 32 + lane;            // accumulator row inside the tile
         const int ww = r % p.tw, hh = (r / p.tw) % p.th, bb = r / (p.tw * p.th);
         const int mode = p.mode;
@@ -292,18 +297,18 @@ __global__ void __launch_bounds__(kThreadsGemm, CR ? 2 : 1) gemm_tc_kernel(const
             const long long row = ((long long)b * p.H + y) * p.W + x;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
             if (mode == 0) {
-                constexpr int NCH = BN / 32;                 // 32-column chunks of the tile
-                constexpr int NCH0 = (NCH + 1) / 2;          // chunks of part 0
-                constexpr int NPER = NCH0;                   // max chunks per warp
-                const int c_begin = part ? NCH0 : 0, c_end = part ? NCH : NCH0;
+                constexpr int NCH = BN / 16;                      // 16-column chunks of the tile
+                constexpr int NPER = (NCH + kEpiParts - 1) / kEpiParts;   // chunks per warp (the last part may get fewer)
+                const int c_begin = part * NPER;
+                const int c_end = (c_begin + NPER < NCH) ? c_begin + NPER : NCH;
                 const int n_base = n_tile * BN;
                 const __half* res_row = p.res ? p.res + row * p.ldr : nullptr;
                 // residual of the first chunk: requested BEFORE the accumulator is complete (overlaps the MMAs)
-                uint4 rnext[4];
-                auto load_res = [&](int c, uint4 (&dst)[4]) {
+                uint4 rnext[2];
+                auto load_res = [&](int c, uint4 (&dst)[2]) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int n = n_base + c * 32 + g * 8;
+                    for (int g = 0; g < 2; ++g) {
+                        const int n = n_base + c * 16 + g * 8;
                         dst[g] = (res_row && row_ok && n < p.N) ? *reinterpret_cast<const uint4*>(res_row + n)
                                                                : make_uint4(0, 0, 0, 0);
                     }
@@ -318,17 +323,17 @@ __global__ void __launch_bounds__(kThreadsGemm, CR ? 2 : 1) gemm_tc_kernel(const
                 for (int i = 0; i < NPER; ++i) {
                     const int c = c_begin + i;
                     if (c < c_end) {                    // warp-uniform
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(t_addr + c * 32, v);
-                        uint4 rcur[4];
+                        uint32_t v[16];
+                        tmem_ld_32x32b_x16(t_addr + c * 16, v);
+                        uint4 rcur[2];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+                        for (int g = 0; g < 2; ++g) rcur[g] = rnext[g];
                         if (c + 1 < c_end) load_res(c + 1, rnext);   // in flight while this chunk is processed
                         tmem_ld_wait();
-                        const int n0 = n_base + c * 32;
+                        const int n0 = n_base + c * 16;
                         if (row_ok && n0 < p.N) {
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
+                            for (int g = 0; g < 2; ++g) {
                                 const int n = n0 + g * 8;
                                 if (n < p.N) {      // N is a multiple of 8 (checked on the host)
                                     float acc8[8];
@@ -380,14 +385,15 @@ __global__ void __launch_bounds__(kThreadsGemm, CR ? 2 : 1) gemm_tc_kernel(const
                     }
                 }
                 if (p.stats_out && row_ok)
-                    p.stats_out[row * (2 * p.tiles_n) + 2 * n_tile + part] = make_float2(st_sum, st_sq);
+                    p.stats_out[row * (kEpiParts * p.tiles_n) + kEpiParts * n_tile + part] = make_float2(st_sum, st_sq);
             } else {
                 // GEGLU: tile columns [0,BN/2) are "value", [BN/2,BN) the matching "gate" (weights are
                 // row-interleaved per tile on the host); out = (v+bv) * gelu(g+bg), BN/2 outputs per tile.
                 constexpr int HN = BN / 2;
-                constexpr int NCH = HN / 32;
-                constexpr int NCH0 = (NCH + 1) / 2;
-                const int c_begin = part ? NCH0 : 0, c_end = part ? NCH : NCH0;
+                constexpr int NCH = HN / 16;
+                constexpr int NPER = (NCH + kEpiParts - 1) / kEpiParts;
+                const int c_begin = part * NPER;
+                const int c_end = (c_begin + NPER < NCH) ? c_begin + NPER : NCH;
                 const int o_base = n_tile * HN;        // output column base
                 const int a_base = n_tile * BN;        // accumulator (bias) column base
                 float ln_mu = 0.f, ln_rstd = 1.f;
@@ -396,15 +402,15 @@ __global__ void __launch_bounds__(kThreadsGemm, CR ? 2 : 1) gemm_tc_kernel(const
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = c_begin; c < c_end; ++c) {
-                    uint32_t vv[32], vg[32];
-                    tmem_ld_32x32b_x32(t_addr + c * 32, vv);
-                    tmem_ld_32x32b_x32(t_addr + HN + c * 32, vg);
+                    uint32_t vv[16], vg[16];
+                    tmem_ld_32x32b_x16(t_addr + c * 16, vv);
+                    tmem_ld_32x32b_x16(t_addr + HN + c * 16, vg);
                     tmem_ld_wait();
                     if (row_ok) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
+                        for (int g = 0; g < 2; ++g) {
                             float bv[8], bg[8];
-                            const int jn = c * 32 + g * 8;
+                            const int jn = c * 16 + g * 8;
                             if (p.ln_stats) {
                                 float cv[8], cg[8];
                                 load8f(p.ln_csum + a_base + jn, cv);
@@ -544,10 +550,7 @@ template <int BN, int CL, int CR> int launch_bn_cl(const GemmPlan& plan, cudaStr
 }
 template <int BN> int launch_bn(const GemmPlan& plan, cudaStream_t st) {
     if (plan.cluster == 2) return launch_bn_cl<BN, 2, 0>(plan, st);
-    if constexpr (BN <= 160) {
-        if (plan.coresident) return launch_bn_cl<BN, 1, 1>(plan, st);
-    }
-    return launch_bn_cl<BN, 1, 0>(plan, st);
+    return launch_bn_cl<BN, 1, 0>(plan, st);      // (the CR = 1 co-resident variant is no longer instantiated, see below)
 }
 
 }  // namespace
@@ -654,8 +657,8 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
     }
     if (d.stats_out) {
         LB_REQUIRE(p.mode == 0, "gemm: stats_out needs the linear epilogue");
-        LB_REQUIRE(d.stats_parts == 2 * p.tiles_n, "gemm: stats_parts must be 2 * ceil(N / %d) = %d (got %d)", bn,
-                   2 * p.tiles_n, d.stats_parts);
+        LB_REQUIRE(d.stats_parts == kEpiParts * p.tiles_n, "gemm: stats_parts must be %d * ceil(N / %d) = %d (got %d)",
+                   kEpiParts, bn, kEpiParts * p.tiles_n, d.stats_parts);
         p.stats_out = static_cast<float2*>(d.stats_out);
     }
     // CTA pairs (cta_group::2, M = 256) whenever there are at least two M tiles
@@ -676,17 +679,11 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
         const int tiles = p.tiles_m * p.tiles_n;
         plan->grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
     }
-    // co-resident variant: single-wave problems (one tile per CTA) on the single-CTA path
-    {
-        const char* cr_env = getenv("LB_GEMM_CORESIDENT");
-        const bool single_wave = (int64_t)p.tiles_m * p.tiles_n <= ctx->sm_count;
-        // Measured (r02b): with only 3 ring stages the TMA round trip (~1900 clk vs 256-320 clk per k-block) is no longer
-        // hidden -- conv 2048x1280x11520 45 -> 75 us, to_out 2048x1280x1280 11.6 -> 16.2 us, UNet step 23.5 -> 26.1 ms.
-        // The variant therefore stays OFF unless LB_GEMM_CORESIDENT=1 asks for it (kept for the record of the experiment).
-        (void)single_wave;
-        plan->coresident = 0;
-        if (cr_env) plan->coresident = (atoi(cr_env) != 0 && plan->cluster == 1 && plan->bn <= 160 && single_wave) ? 1 : 0;
-    }
+    // The co-resident variant (CR = 1: 3-stage ring, one accumulator, two CTAs per SM) was measured in r02b and dropped:
+    // with only 3 ring stages the TMA round trip (~1900 clk vs 256-320 clk per k-block) is no longer hidden -- conv
+    // 2048x1280x11520 45 -> 75 us, to_out 2048x1280x1280 11.6 -> 16.2 us, UNet step 23.5 -> 26.1 ms
+    // (profiles/r02b_bench_ops_coresident_on.txt).
+    plan->coresident = 0;
     // ring depth: deep for long-K problems (>= 40 k-blocks: the 3x3 convolutions, FF-out), shallow otherwise
     {
         const bool deep = total >= 40 && !getenv("LB_GEMM_SHALLOW");
@@ -694,7 +691,6 @@ int gemm_plan_build(lb_ctx* ctx, const GemmDesc& d, GemmPlan* plan) {
         const int shallow_st = (bnv <= 64) ? 8 : (bnv <= 128) ? 6 : (bnv <= 160) ? 5 : 4;
         const int deep_st = (bnv <= 64) ? 8 : (bnv <= 128) ? 7 : (bnv <= 160) ? 6 : 4;
         p.stages = deep ? deep_st : shallow_st;
-        if (plan->coresident) p.stages = (bnv <= 64) ? 4 : 3;
     }
     plan->smem_bytes = 0;
     return 0;
@@ -717,7 +713,7 @@ extern "C" int lb_gemm_stats_parts(lb_ctx* ctx, const lb_gemm_desc* desc) {
     d.stats_out = nullptr;
     GemmPlan plan;
     if (gemm_plan_build(ctx, d, &plan)) return -1;
-    return 2 * plan.p.tiles_n;
+    return kEpiParts * plan.p.tiles_n;
 }
 
 extern "C" int lb_gemm(lb_ctx* ctx, const lb_gemm_desc* desc, void* stream) {

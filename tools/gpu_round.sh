@@ -43,6 +43,11 @@ small)
 ncu_small)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gn_|ln_kernel|cfg_euler|scale_input|embed_inputs" -c 24 -o $O/small -f \
      env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_small.py > $O/ncu_small.log 2>&1; echo "ncu small exit $?" ;;
+ncu_pair)
+  for c in 1 2; do
+    LB_GEMM_CLUSTER=$c timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 3 -c 1 -o $O/ffin_cl$c -f \
+       env BENCH_ITERS=1 BENCH_WARM=0 python tools/bench_ops.py gemm > $O/ncu_pair_$c.log 2>&1; echo "ncu pair $c exit $?"
+  done ;;
 gemmsplit)
   # which side bounds a GEMM: LB_GEMM_DEBUG=1 skips the TMA loads (MMA + epilogue only), =2 skips the MMA issue (TMA + epilogue only)
   : > $O/gemm_split.txt
