@@ -106,7 +106,7 @@ int lb_cfg_euler_step(lb_ctx* ctx, const void* latents_dev, const void* eps_dev,
  * ln_bias[n] = sum_k beta[k] w[n,k] + bias[n] prepared once on the host,
  *     LN(x) w^T + bias  ==  rstd_m * (x w'^T - mu_m * ln_csum) + ln_bias,
  * where (mu_m, rstd_m) come from ln_stats[m][0..ln_parts) = per-row partial (sum, sum of squares) that the GEMM which
- * PRODUCED x wrote through its stats_out (of its stored fp16 values; stats_parts = 2 * ceil(N / its N tile), reported
+ * PRODUCED x wrote through its stats_out (of its stored fp16 values; stats_parts = 4 * ceil(N / its N tile), reported
  * by lb_gemm_stats_parts).  Fixed summation order: results do not depend on the batch size.
  * Replaces the cuBLAS / cuDNN calls under pipe.unet(...)
  * (diffusers_holder.py:336-344).  Constraints: a0_c, a1_c multiples of 64;
@@ -138,7 +138,8 @@ typedef struct lb_gemm_desc {
  * instead of per 128-row tile; the kernel then runs N = 256 MMAs (fewer shared-memory operand reads per FLOP) */
 #define LB_GEMM_GEGLU256 0x400
 int lb_gemm(lb_ctx* ctx, const lb_gemm_desc* desc, void* stream);
-/* number of per-row partials a GEMM with this desc writes through stats_out (2 per N tile); < 0 on error */
+/* number of per-row partials a GEMM with this desc writes through stats_out (4 per N tile: one per epilogue warp of a
+ * TMEM lane quadrant); < 0 on error */
 int lb_gemm_stats_parts(lb_ctx* ctx, const lb_gemm_desc* desc);
 
 /* ---- K8: fused attention, head_dim 64 ----------------------------------------

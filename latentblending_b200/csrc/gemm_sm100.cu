@@ -10,16 +10,17 @@
 // by (dy,dx) with hardware zero fill at the borders -- no im2col buffer), and
 // the resnet shortcut folded in as an extra K-segment from a second tensor.
 //
-// Structure (one CTA per SM, persistent over output tiles, 320 threads):
+// Structure (one CTA per SM, persistent over output tiles, 576 threads):
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor 4D (A) / 2D (W) into a
 //              STAGES-deep 128B-swizzled smem ring, mbarrier full/empty pairs
 //   warp 1   : MMA issuer    -- one thread issues tcgen05.mma (M=128, N=BN,
 //              K=16, fp16 in / fp32 accumulate in TMEM), tcgen05.commit frees
 //              smem slots and publishes the accumulator
-//   warps 2-9: epilogue      -- tcgen05.ld TMEM->registers, + bias / per-batch
-//              bias (time embedding) / residual, or GEGLU, fp16 store; two warps
-//              per TMEM lane quadrant split the tile's columns (the GEGLU / residual
-//              epilogue of one warp per scheduler was as long as the tile's MMAs);
+//   warps 2-17: epilogue     -- tcgen05.ld TMEM->registers, + bias / per-batch
+//              bias (time embedding) / residual, or GEGLU, fp16 store; FOUR warps
+//              per TMEM lane quadrant split the tile's 16-column chunks (r02r/r02s: with
+//              two warps per quadrant the epilogue was latency-bound at 0.39 IPC and the
+//              exposed drain of the single-tile launches cost ~1.4 ms per UNet forward);
 //              residual rows are prefetched while the accumulator is still being
 //              produced; double-buffered accumulators overlap the epilogue with the
 //              next tile's MMAs

@@ -146,7 +146,7 @@ def gemm(a0, w, N, B, H, W, taps=1, a0_c=None, a1=None, a1_c=None, bias=None, bi
 
 
 def gemm_stats_parts(a0, w, N, B, H, W, **kw):
-    """Per-row partial count of lb_gemm's stats_out for this problem (2 per N tile)."""
+    """Per-row partial count of lb_gemm's stats_out for this problem (4 per N tile)."""
     import ctypes
     dev = _dev(a0)
     d = _cabi.GemmDesc()

@@ -418,8 +418,9 @@ class UNetB200:
         if fold_ln is None:
             fold_ln = os.environ.get("LB_LN_FOLD") is not None
         self.fold_ln = fold_ln
-        # GEGLU N tile: 256 when every FF inner width allows it (4*C % 128 == 0) and LB_GEGLU_TILE does not say otherwise
-        tile = int(os.environ.get("LB_GEGLU_TILE", "128"))
+        # GEGLU N tile: 256 (N = 256 MMAs re-read the activation tile half as often) when every FF width allows it;
+        # same-box A/B with the 16-warp epilogue (r02t): 20.35 -> 20.12 ms per forward.  LB_GEGLU_TILE=128 restores 128.
+        tile = int(os.environ.get("LB_GEGLU_TILE", "256"))
         widths = [c for c, d in zip(cfg.block_out_channels, cfg.transformer_layers) if d]
         if tile == 256 and any((8 * c) % 256 for c in widths):
             tile = 128

@@ -81,6 +81,10 @@ cluster2)
 dual)
   timeout 300 python tools/time_dual_stream.py > $O/dual_stream.txt 2>&1; cat $O/dual_stream.txt
   LB_GEMM_CORESIDENT=0 timeout 300 python tools/time_dual_stream.py > $O/dual_stream_nocr.txt 2>&1; cat $O/dual_stream_nocr.txt ;;
+geglu)
+  : > $O/geglu_ab.txt
+  for e in "" "LB_GEGLU_TILE=256" "" "LB_GEGLU_TILE=256"; do env $e timeout 300 python tools/time_unet_batch.py 2 >> $O/geglu_ab.txt 2>&1; done
+  cat $O/geglu_ab.txt ;;
 ab)
   # same-box A/B of the UNet step (batch 2): default | no LN fold | no graph | GEGLU tile 256 | no PDL
   : > $O/ab.txt
