@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from latentblending_b200.sharding import LevelSharder, older_parents, plan_candidates
+from latentblending_b200.sharding import LevelSharder, older_parents, plan_candidates, run_level_local
 
 
 class Tree:
@@ -164,3 +164,30 @@ def test_plan_candidates_first_is_reference_choice():
     assert all(x[0] != 0.375 for x in c2)
     # the very first insertion: a 1-list holding a non-number (blending_engine.py:349)
     assert plan_candidates([0.0, 1.0], [None], 3, {})[0] == (0.5, 0.0, 1.0)
+
+
+@pytest.mark.parametrize("width", [2, 3, 4])
+@pytest.mark.parametrize("seed", [7, 8, 9])
+def test_local_lockstep_speculation_equals_sequential(width, seed):
+    """run_level_local (the single-GPU form of the same plan / replay: candidates share one batched forward) builds the
+    reference's sequential tree whatever the width and however many candidates miss; on_insert sees the insertions in
+    the sequential order; the adaptive split ratio is carried from level to level."""
+    N, levels = 30, [(15, 4), (18, 3), (21, 3), (24, 2), (27, 1)]
+    ref = sequential(N, levels, seed)
+    tree = Tree(N, seed)
+    comp = make_compute(tree, N)
+    batches = []
+
+    def many(cands, idx):
+        batches.append(len(cands))
+        return [comp(m, p1, p2, idx) for m, p1, p2 in cands]
+    stats, inserted, ratio = dict(rounds=0, computed=0, used=0), [], 0.6
+    for idx, stems in levels:
+        ratio = run_level_local(tree, idx, stems, many, sim, width, on_insert=inserted.append, stats=stats,
+                                split_ratio=ratio)
+    assert tree.tree_fracts == ref.tree_fracts and tree.tree_idx_injection == ref.tree_idx_injection
+    np.testing.assert_allclose(tree.tree_similarities, ref.tree_similarities, rtol=0, atol=0)
+    assert [float(t[-1].float().sum()) for t in tree.tree_latents] == [float(t[-1].float().sum()) for t in ref.tree_latents]
+    assert inserted == ref.insert_order
+    assert stats["used"] == 13 and stats["computed"] >= 13 and stats["rounds"] == len(batches)
+    assert max(batches) <= width and 0.0 < ratio <= 1.0
