@@ -18,7 +18,7 @@ from collections import OrderedDict
 import torch
 
 from . import _cabi, ops
-from ._cabi import GEMM_RELU, ctx
+from ._cabi import ctx
 from .unet import Program
 
 _LP_SHIFT = (-0.030, -0.088, -0.188)
