@@ -201,3 +201,62 @@ def test_engine_refuses_random_lpips_for_real_weights():
     dh.pipe = RealPipe()
     with pytest.raises(ValueError, match="lpips_state_dict"):
         BlendingEngine(RealPipe(), holder=dh, run_benchmark=False)
+
+
+def test_layernorm_fold_algebra_and_geglu_permutation_on_cpu():
+    """Host-side packing of the optional LayerNorm fold (unet._fold_layernorm) and of the GEGLU row interleave
+    (unet._geglu_perm), checked in fp32 on the CPU against torch's LayerNorm + Linear + exact-erf GEGLU: the kernel
+    computes rstd*(x W'^T - mu*csum) + lnb per row, and reads value / gate rows per N tile."""
+    import torch.nn.functional as F
+    from latentblending_b200.unet import _fold_layernorm, _geglu_perm
+    g = torch.Generator().manual_seed(0)
+    M, C, N = 37, 128, 512
+    x = torch.randn(M, C, generator=g) * 2 + 0.5
+    w = (torch.randn(N, C, generator=g) * C ** -0.5).half()
+    b = (torch.randn(N, generator=g) * 0.1).half()
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).half()
+    beta = (0.05 * torch.randn(C, generator=g)).half()
+    wf, csum, lnb = _fold_layernorm(w, b, gamma, beta)
+    assert wf.dtype == torch.float16 and csum.dtype == lnb.dtype == torch.float32
+    mu = x.mean(1, keepdim=True)
+    rstd = (x.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    got = rstd * (x @ wf.float().t() - mu * csum[None, :]) + lnb[None, :]
+    want = F.layer_norm(x, (C,), gamma.float(), beta.float(), 1e-5) @ w.float().t() + b.float()
+    # the only difference is the fp16 rounding of w*gamma
+    assert ((got - want).norm() / want.norm()).item() < 1e-3
+    # GEGLU interleave: tile t of `half` value rows is followed by its `half` gate rows
+    for half in (64, 128):
+        perm = _geglu_perm(N // 2, "cpu", half=half)
+        assert sorted(perm.tolist()) == list(range(N))
+        y = want[:, perm]                                    # what the kernel's accumulator columns hold
+        tiles = y.view(M, -1, 2 * half)
+        out = (tiles[:, :, :half] * F.gelu(tiles[:, :, half:])).reshape(M, N // 2)
+        v, gate = want.chunk(2, dim=-1)
+        assert torch.allclose(out, v * F.gelu(gate), atol=1e-6)
+
+
+def test_bench_helpers():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert abs(bench.unet_tflop(128) - 6.761) < 1e-3                  # SURVEY 8d, exact at the bench shape
+    assert abs(bench.unet_tflop(64) / 1.589 - 1) < 0.03               # pixel / pixel^2 scaling model vs the analytic 512^2 count
+    assert 1 <= bench.host_cpu_budget() <= (os.cpu_count() or 1)
+    for c in (2, 3, 5):
+        cfg = bench.CONFIGS[c]
+        assert cfg["frames"] == sum(cfg["stems"]) + 2 and cfg["metric"] and cfg["workload"]
+    # forwards of the base configs: 2 outer trajectories x N + sum stems x (N - idx_injection)
+    idx = [15, 18, 21, 24, 27]
+    for c in (2, 3):
+        cfg = bench.CONFIGS[c]
+        assert cfg["unet_forwards"] == 2 * 30 + sum(s * (30 - i) for s, i in zip(cfg["stems"], idx))
+    assert bench.CONFIGS[5]["unet_forwards"] == 2 * 4 + 60 * 2
+
+    class FakeEngine:
+        tree_fracts = [0.0, 0.5, 1.0]
+        tree_idx_injection = [0, 2, 0]
+        tree_latents = [[torch.zeros(4)], [torch.ones(4)], [torch.zeros(4)]]
+    a = bench.tree_fingerprint(FakeEngine())
+    FakeEngine.tree_latents[1][0][0] = 2.0
+    assert a != bench.tree_fingerprint(FakeEngine()) and len(a) == 40
